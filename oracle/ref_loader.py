@@ -1,0 +1,132 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference loss by file path.
+
+mmlearn cannot be imported as a package in this image (hydra_zen, lightning, torchmetrics,
+timm, peft are not installed and there is no wheel for them; hatchling is missing too, so
+``pip install /root/reference`` fails).  The reference source files themselves are pure
+Python on top of torch, so they run in place once the missing imports are stubbed:
+
+* ``hydra_zen.store``            -> identity decorator (``@store`` and ``@store(group=...)``)
+* ``torchmetrics.utilities.compute._safe_matmul`` -> restated from torchmetrics 1.6.2
+  (pinned in the reference's ``uv.lock``): fp16 inputs are up-cast, everything else is
+  ``x @ y.T``.  Call sites: ``mmlearn/modules/losses/contrastive.py:327,330,334,339,340``.
+* ``lightning.fabric.utilities.rank_zero_warn`` -> ``warnings.warn``
+
+Only available where ``/root/reference`` exists (the authoring container).  It is used by
+``oracle/make_golden.py`` to produce ``tests/golden/*.npz`` and by the CPU tests that pin
+``oracle/contrastive_oracle.py`` against the real reference.  Nothing in the product imports it.
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+import warnings
+from dataclasses import dataclass
+
+REFERENCE_ROOT = os.environ.get("MMLEARN_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(
+        os.path.join(REFERENCE_ROOT, "mmlearn/modules/losses/contrastive.py")
+    )
+
+
+def _load(name: str, relpath: str) -> types.ModuleType:
+    spec = importlib.util.spec_from_file_location(
+        name, os.path.join(REFERENCE_ROOT, relpath)
+    )
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_CACHE: dict[str, types.ModuleType] = {}
+
+
+def load_reference() -> dict[str, types.ModuleType]:
+    """Return {"contrastive": module, "example": module, "modalities": module}."""
+    if _CACHE:
+        return _CACHE
+    if not reference_available():
+        raise RuntimeError(f"reference sources not found under {REFERENCE_ROOT}")
+    import torch
+
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split(".")[0] in
+             ("mmlearn", "hydra_zen", "torchmetrics", "lightning")}
+
+    # --- stubs -------------------------------------------------------------------------
+    hz = types.ModuleType("hydra_zen")
+
+    def store(*args, **kwargs):
+        if len(args) == 1 and callable(args[0]) and not kwargs:
+            return args[0]
+        return lambda obj: obj
+
+    hz.store = store
+    hz.MISSING = object()
+    sys.modules["hydra_zen"] = hz
+
+    tm = types.ModuleType("torchmetrics")
+    tmu = types.ModuleType("torchmetrics.utilities")
+    tmc = types.ModuleType("torchmetrics.utilities.compute")
+
+    def _safe_matmul(x, y):
+        if x.dtype == torch.float16 or y.dtype == torch.float16:
+            return (x.float() @ y.T.float()).half()
+        return x @ y.T
+
+    tmc._safe_matmul = _safe_matmul
+    tm.utilities = tmu
+    tmu.compute = tmc
+    sys.modules["torchmetrics"] = tm
+    sys.modules["torchmetrics.utilities"] = tmu
+    sys.modules["torchmetrics.utilities.compute"] = tmc
+
+    li = types.ModuleType("lightning")
+    lf = types.ModuleType("lightning.fabric")
+    lfu = types.ModuleType("lightning.fabric.utilities")
+    lfu.rank_zero_warn = lambda msg, *a, **k: warnings.warn(msg)
+    li.fabric = lf
+    lf.utilities = lfu
+    sys.modules["lightning"] = li
+    sys.modules["lightning.fabric"] = lf
+    sys.modules["lightning.fabric.utilities"] = lfu
+
+    # package placeholders so the heavy __init__ files are skipped
+    for pkg in ("mmlearn", "mmlearn.datasets", "mmlearn.datasets.core", "mmlearn.tasks",
+                "mmlearn.modules", "mmlearn.modules.losses"):
+        m = types.ModuleType(pkg)
+        m.__path__ = []  # type: ignore[attr-defined]
+        sys.modules[pkg] = m
+
+    modalities = _load("mmlearn.datasets.core.modalities", "mmlearn/datasets/core/modalities.py")
+    example = _load("mmlearn.datasets.core.example", "mmlearn/datasets/core/example.py")
+    core = sys.modules["mmlearn.datasets.core"]
+    core.find_matching_indices = example.find_matching_indices
+    core.Modalities = modalities.Modalities
+    core.modalities = modalities
+    core.example = example
+
+    # LossPairSpec lives in the task file, which drags in Lightning; the dataclass is 3 lines
+    # (mmlearn/tasks/contrastive_pretraining.py:44-52) and is only used as a type + attribute bag.
+    cp = types.ModuleType("mmlearn.tasks.contrastive_pretraining")
+
+    @dataclass
+    class LossPairSpec:
+        modalities: tuple
+        weight: float = 1.0
+
+    cp.LossPairSpec = LossPairSpec
+    sys.modules["mmlearn.tasks.contrastive_pretraining"] = cp
+
+    contrastive = _load(
+        "mmlearn.modules.losses.contrastive", "mmlearn/modules/losses/contrastive.py"
+    )
+    _CACHE.update(
+        contrastive=contrastive, example=example, modalities=modalities, task_stub=cp
+    )
+    return _CACHE
