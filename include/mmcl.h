@@ -1,0 +1,159 @@
+/*
+ * mmcl.h -- C ABI of the B200 (sm_100a) contrastive-loss hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every function
+ * returns 0 on success and a negative mmcl_status otherwise; none throws, aborts, allocates
+ * device memory or synchronises the device (except where stated).  All device work is enqueued
+ * on the caller-supplied stream.  The caller owns every buffer.  A handle may be used from
+ * several host threads (forward on the main thread, backward on PyTorch's autograd thread);
+ * calls on one handle are serialised internally.  mmcl_last_error() is thread-local.
+ *
+ * "Replaces" cites the reference interface each entry point stands in for; paths are relative
+ * to the mmlearn source tree (mmlearn 0.1.0b2).
+ */
+#ifndef MMCL_H_
+#define MMCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMCL_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  MMCL_OK = 0,
+  MMCL_ERR_INVALID = -1,   /* bad argument (null pointer, unsupported shape/dtype) */
+  MMCL_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed (message has the string) */
+  MMCL_ERR_NCCL = -3,      /* an NCCL call failed */
+  MMCL_ERR_WORKSPACE = -4, /* workspace_bytes too small; see the *_workspace_bytes query */
+  MMCL_ERR_ARCH = -5       /* device is not compute capability 10.x */
+} mmcl_status;
+
+typedef enum { MMCL_F32 = 0, MMCL_BF16 = 1, MMCL_F16 = 2 } mmcl_dtype;
+
+typedef struct mmcl_handle mmcl_handle;
+typedef void* mmcl_stream; /* cudaStream_t */
+
+int mmcl_version(void);
+const char* mmcl_last_error(void);
+
+/* Size of the opaque NCCL unique id (ncclUniqueId) the caller broadcasts to all ranks. */
+#define MMCL_NCCL_UID_BYTES 128
+/* Rank 0 fills `uid` (host memory); the caller ships it to every rank (torch.distributed). */
+int mmcl_nccl_unique_id(void* uid);
+
+/*
+ * One handle per process/GPU.  world == 1: `nccl_uid` may be NULL and no communicator is
+ * created.  world > 1: collective -- every rank must call it with the same uid.
+ * Replaces: the implicit torch.distributed default group used by
+ * mmlearn/modules/losses/contrastive.py:86-87,457-458.
+ */
+int mmcl_create(mmcl_handle** out, int device, int rank, int world, const void* nccl_uid);
+int mmcl_destroy(mmcl_handle* h);
+
+/* ------------------------------------------------------------------------------------------
+ * Example-id matching.
+ * Replaces: mmlearn/datasets/core/example.py:101-166 find_matching_indices (called at
+ * contrastive.py:279-282 and :310-313).  ids_* are int64 [n,2] / [m,2] row-major on the device.
+ * Output order is torch.where's: ascending index into a, then ascending index into b;
+ * duplicate ids yield the cross product (reference test tests/datasets/test_example.py:159-168).
+ * At most `capacity` pairs are written to out_a/out_b; out_info (device int64[2]) receives
+ * {k = total number of matches, identity = 1 iff n == m and the result is (arange, arange)}.
+ * The caller reads out_info (its only host sync) and retries with capacity >= k if needed.
+ * ------------------------------------------------------------------------------------------ */
+size_t mmcl_match_workspace_bytes(int64_t n, int64_t m);
+int mmcl_match_ids(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_t* ids_b,
+                   int64_t m, int64_t* out_a, int64_t* out_b, int64_t capacity,
+                   int64_t* out_info, void* workspace, size_t workspace_bytes,
+                   mmcl_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row packing: dst[i,:] = bf16( normalise?( src[idx[i],:] ) ), inv_norm[i] = 1/max(|src row|,1e-12)
+ * (1.0 when normalize == 0).  idx == NULL means idx[i] = i.
+ * Replaces: F.normalize at contrastive.py:89-90 and the row selection `emb[indices]` at
+ * contrastive.py:290-291,318-319; writes straight into the caller's gather buffer.
+ * ------------------------------------------------------------------------------------------ */
+int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_rows, int64_t d,
+                   const int64_t* idx, int64_t n_out, int normalize, void* dst_bf16,
+                   float* inv_norm, mmcl_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Collectives over the handle's NCCL communicator (NVLink / NVSwitch).  counts[r] = number of
+ * ROWS rank r contributes / receives; rows are `row_bytes` wide.  Uneven counts are supported
+ * (grouped broadcasts / reduces).  world == 1: a device-to-device copy.
+ * Replaces: _gather_dicts / _gather_all_tensors / _simple_gather_all_tensors at
+ * contrastive.py:431-578 (all-gather, and the reduce-scatter that autograd's all-gather
+ * performs in backward, contrastive.py:506).
+ * ------------------------------------------------------------------------------------------ */
+int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int64_t* counts,
+                         int64_t row_bytes, mmcl_stream stream);
+int mmcl_reduce_scatter_rows_f32(mmcl_handle* h, const float* send, float* recv,
+                                 const int64_t* counts, int64_t row_floats, mmcl_stream stream);
+int mmcl_all_reduce_sum_f32(mmcl_handle* h, float* buf, int64_t n, mmcl_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused similarity + online log-sum-exp (forward hot kernel, tcgen05/TMEM/TMA).
+ * For q [nq,d], k [nk,d] (bf16 row-major, d % 8 == 0) and s = *scale (device fp32):
+ *   lse[i]  = log sum_j exp(s * q_i . k_j)
+ *   esum[i] = sum_j softmax_j(s * q_i . k_j) * (s * q_i . k_j)       (gives d loss / d s)
+ * The nq x nk logit matrix only ever exists as 128x128 fp32 tiles in tensor memory.
+ * Replaces: _safe_matmul + logit_scale multiply (contrastive.py:327-340) and the
+ * log-softmax half of F.cross_entropy (contrastive.py:138-139).
+ * ------------------------------------------------------------------------------------------ */
+size_t mmcl_sim_lse_workspace_bytes(mmcl_handle* h, int64_t nq, int64_t nk, int64_t d);
+int mmcl_sim_lse_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                     int64_t nk, int64_t d, const float* scale, float* lse, float* esum,
+                     void* workspace, size_t workspace_bytes, mmcl_stream stream);
+
+/* pos[i] = s * q_i . k_{label_offset + i}  (the positive logit; labels are off_r + i,
+ * contrastive.py:194-212).  fp32 accumulation over the same bf16 rows the GEMM reads. */
+int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                         int64_t nk, int64_t d, int64_t label_offset, const float* scale,
+                         float* pos, mmcl_stream stream);
+
+/* Pair loss and d loss / d s from the row statistics of both directions
+ * (contrastive.py:135-144):  out[0] += weight/(2 n) * sum_i (lse_a+lse_b-2 pos)[i]
+ *                            out[1] += weight/(2 n) / s * sum_i (esum_a+esum_b-2 pos)[i]
+ * `n_norm` is the divisor (local matched rows for local_loss, global rows otherwise). */
+int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const float* esum_a,
+                   const float* esum_b, const float* pos, int64_t n, double weight, double n_norm,
+                   const float* scale, float* out2, mmcl_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused recompute backward (hot kernel, tcgen05/TMEM/TMA): for x [nx,d], y [ny,d] bf16 and
+ * c = s*log2(e):
+ *   dx[i,:] += sum_j ( 2^(c x_i.y_j - off_row[i]) + 2^(c x_i.y_j - off_col[j]) ) * y[j,:]
+ * Either offset vector may be NULL (term dropped).  With off_row = log2(e)*lse_row + log2(2 b)
+ * the first term is softmax_row/(2b); with off_col likewise the column-normalised softmax.
+ * dx is fp32 [nx,d] and must be zero-initialised (or hold a running sum) by the caller.
+ * Replaces: autograd's backward through cross_entropy, the scale multiply and both matmuls
+ * (contrastive.py:327-340,138-139); logit tiles are recomputed, never stored.
+ * ------------------------------------------------------------------------------------------ */
+int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16,
+                      int64_t ny, int64_t d, const float* scale, const float* off_row,
+                      const float* off_col, float* dx, mmcl_stream stream);
+
+/* off[i] = log2(e) * lse[i] + log2(denom[i] or denom_scalar)  (helper for the call above) */
+int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* denom_vec,
+                      double denom_scalar, float* off, mmcl_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient unpack for one modality side of one pair:
+ *   g_hat[i,:] = coef * ( dacc[i,:] - pos_coef * partner[i,:] )        coef = weight*(*gout)*(*s)
+ *   g[i,:]     = normalise-backward(g_hat[i,:]; src row, inv_norm[i])  (if normalize)
+ *   grad[idx[i],:] += g[i,:]                                           (fp32 atomics)
+ * Replaces: backward of index-select (index_put accumulate), of F.normalize and the
+ * positive-label term of cross_entropy's backward.
+ * ------------------------------------------------------------------------------------------ */
+int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16, int64_t n,
+                     int64_t d, double weight, double pos_coef, const float* gout,
+                     const float* scale, const void* src, int src_dtype, const float* inv_norm,
+                     int normalize, const int64_t* idx, float* grad_f32, mmcl_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMCL_H_ */

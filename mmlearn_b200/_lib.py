@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI in ``include/mmcl.h`` (``mmlearn_b200/libmmcl.so``).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmcl.so")
+
+#: every symbol include/mmcl.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mmcl_version": (c_int, []),
+    "mmcl_last_error": (c_char_p, []),
+    "mmcl_nccl_unique_id": (c_int, [c_void_p]),
+    "mmcl_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p]),
+    "mmcl_destroy": (c_int, [c_void_p]),
+    "mmcl_match_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "mmcl_match_ids": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                               c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmcl_pack_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64,
+                               c_int, c_void_p, c_void_p, c_void_p]),
+    "mmcl_all_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64,
+                                     c_void_p]),
+    "mmcl_reduce_scatter_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64),
+                                             c_int64, c_void_p]),
+    "mmcl_all_reduce_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "mmcl_sim_lse_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64, c_int64]),
+    "mmcl_sim_lse_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmcl_positive_logits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                     c_int64, c_void_p, c_void_p, c_void_p]),
+    "mmcl_pair_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                               c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "mmcl_sim_grad_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmcl_make_offsets": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_double, c_void_p,
+                                  c_void_p]),
+    "mmcl_unpack_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
+                                 c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_void_p]),
+}
+
+NCCL_UID_BYTES = 128
+_lib = None
+
+
+class MmclError(RuntimeError):
+    """A C-ABI call returned a negative mmcl_status."""
+
+
+def load() -> ctypes.CDLL:
+    """Load libmmcl.so and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` "
+            "(nvcc, sm_100a). mmlearn_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mmcl_last_error()
+        raise MmclError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def counts_array(counts) -> ctypes.Array:
+    return (c_int64 * len(counts))(*[int(c) for c in counts])

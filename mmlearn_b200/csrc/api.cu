@@ -1,0 +1,354 @@
+// C ABI (include/mmcl.h): handle, error reporting, NCCL collectives, and thin argument-checking
+// wrappers around the kernel launchers.  No torch types, no device allocation, no device sync.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mmcl.h"
+#include "kernels.h"
+
+using namespace mmcl;
+
+struct mmcl_handle {
+  int device = 0;
+  int rank = 0;
+  int world = 1;
+  int num_sms = 0;
+  ncclComm_t comm = nullptr;
+  std::mutex mu;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  return fail(MMCL_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+int nccl_fail(ncclResult_t r, const char* where) {
+  return fail(MMCL_ERR_NCCL, std::string(where) + ": " + ncclGetErrorString(r));
+}
+
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return fail(MMCL_ERR_INVALID, msg); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int mmcl_version(void) { return MMCL_VERSION; }
+
+const char* mmcl_last_error(void) { return g_err.c_str(); }
+
+int mmcl_nccl_unique_id(void* uid) {
+  REQUIRE(uid, "mmcl_nccl_unique_id: null uid");
+  static_assert(sizeof(ncclUniqueId) == MMCL_NCCL_UID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+  memcpy(uid, &id, sizeof(id));
+  return MMCL_OK;
+}
+
+int mmcl_create(mmcl_handle** out, int device, int rank, int world, const void* nccl_uid) {
+  REQUIRE(out, "mmcl_create: null out");
+  REQUIRE(world >= 1 && rank >= 0 && rank < world, "mmcl_create: bad rank/world");
+  REQUIRE(world == 1 || nccl_uid, "mmcl_create: world > 1 needs an NCCL unique id");
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(MMCL_ERR_ARCH, "mmcl_create: device is sm_" + std::to_string(prop.major) +
+                                   std::to_string(prop.minor) +
+                                   "; this library only contains sm_100a code");
+  auto* h = new mmcl_handle();
+  h->device = device;
+  h->rank = rank;
+  h->world = world;
+  h->num_sms = prop.multiProcessorCount;
+  if (world > 1) {
+    DeviceGuard g(device);
+    ncclUniqueId id;
+    memcpy(&id, nccl_uid, sizeof(id));
+    ncclResult_t r = ncclCommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      delete h;
+      return nccl_fail(r, "ncclCommInitRank");
+    }
+  }
+  *out = h;
+  return MMCL_OK;
+}
+
+int mmcl_destroy(mmcl_handle* h) {
+  if (!h) return MMCL_OK;
+  if (h->comm) ncclCommDestroy(h->comm);
+  delete h;
+  return MMCL_OK;
+}
+
+size_t mmcl_match_workspace_bytes(int64_t n, int64_t m) { return match_workspace_bytes(n, m); }
+
+int mmcl_match_ids(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_t* ids_b,
+                   int64_t m, int64_t* out_a, int64_t* out_b, int64_t capacity, int64_t* out_info,
+                   void* workspace, size_t workspace_bytes, mmcl_stream stream) {
+  REQUIRE(h && out_info, "mmcl_match_ids: null handle/out_info");
+  REQUIRE(n >= 0 && m >= 0 && capacity >= 0, "mmcl_match_ids: negative size");
+  REQUIRE(n < (1ll << 31) && m < (1ll << 31), "mmcl_match_ids: more than 2^31 rows");
+  REQUIRE((n == 0 || ids_a) && (m == 0 || ids_b), "mmcl_match_ids: null ids");
+  REQUIRE(capacity == 0 || (out_a && out_b), "mmcl_match_ids: null outputs");
+  if (n > 0 && m > 0 && workspace_bytes < match_workspace_bytes(n, m))
+    return fail(MMCL_ERR_WORKSPACE, "mmcl_match_ids: workspace too small");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_match_ids(ids_a, n, ids_b, m, out_a, out_b, capacity, out_info, workspace,
+                                   workspace_bytes, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_match_ids");
+}
+
+int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_rows, int64_t d,
+                   const int64_t* idx, int64_t n_out, int normalize, void* dst_bf16,
+                   float* inv_norm, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_pack_rows: null handle");
+  REQUIRE(src_dtype >= 0 && src_dtype <= 2, "mmcl_pack_rows: dtype must be f32/bf16/f16");
+  REQUIRE(d > 0 && d % 8 == 0, "mmcl_pack_rows: d must be a positive multiple of 8");
+  REQUIRE(n_out >= 0 && src_rows >= 0, "mmcl_pack_rows: negative size");
+  REQUIRE(n_out == 0 || (src && dst_bf16), "mmcl_pack_rows: null buffer");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_pack_rows(src, src_dtype, src_rows, d, idx, n_out, normalize, dst_bf16,
+                                   inv_norm, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_pack_rows");
+}
+
+int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int64_t* counts,
+                         int64_t row_bytes, mmcl_stream stream) {
+  REQUIRE(h && counts && row_bytes > 0, "mmcl_all_gather_rows: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (h->world == 1) {
+    if (counts[0] > 0 && send != recv) {
+      cudaError_t e = cudaMemcpyAsync(recv, send, size_t(counts[0]) * row_bytes,
+                                      cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return cuda_fail(e, "mmcl_all_gather_rows");
+    }
+    return MMCL_OK;
+  }
+  bool even = true;
+  for (int r = 1; r < h->world; ++r) even = even && counts[r] == counts[0];
+  ncclResult_t r;
+  if (even) {
+    r = ncclAllGather(send, recv, size_t(counts[0]) * row_bytes, ncclChar, h->comm, st);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
+    return MMCL_OK;
+  }
+  r = ncclGroupStart();
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+  size_t off = 0;
+  for (int root = 0; root < h->world; ++root) {
+    const size_t bytes = size_t(counts[root]) * row_bytes;
+    if (bytes > 0) {
+      r = ncclBroadcast(root == h->rank ? send : nullptr, static_cast<char*>(recv) + off, bytes,
+                        ncclChar, root, h->comm, st);
+      if (r != ncclSuccess) {
+        ncclGroupEnd();
+        return nccl_fail(r, "ncclBroadcast");
+      }
+    }
+    off += bytes;
+  }
+  r = ncclGroupEnd();
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+  return MMCL_OK;
+}
+
+int mmcl_reduce_scatter_rows_f32(mmcl_handle* h, const float* send, float* recv,
+                                 const int64_t* counts, int64_t row_floats, mmcl_stream stream) {
+  REQUIRE(h && counts && row_floats > 0, "mmcl_reduce_scatter_rows_f32: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (h->world == 1) {
+    if (counts[0] > 0 && send != recv) {
+      cudaError_t e = cudaMemcpyAsync(recv, send, size_t(counts[0]) * row_floats * 4,
+                                      cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return cuda_fail(e, "mmcl_reduce_scatter_rows_f32");
+    }
+    return MMCL_OK;
+  }
+  bool even = true;
+  for (int r = 1; r < h->world; ++r) even = even && counts[r] == counts[0];
+  ncclResult_t r;
+  if (even) {
+    r = ncclReduceScatter(send, recv, size_t(counts[0]) * row_floats, ncclFloat, ncclSum, h->comm,
+                          st);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclReduceScatter");
+    return MMCL_OK;
+  }
+  r = ncclGroupStart();
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+  size_t off = 0;
+  for (int root = 0; root < h->world; ++root) {
+    const size_t n = size_t(counts[root]) * row_floats;
+    if (n > 0) {
+      r = ncclReduce(send + off, recv, n, ncclFloat, ncclSum, root, h->comm, st);
+      if (r != ncclSuccess) {
+        ncclGroupEnd();
+        return nccl_fail(r, "ncclReduce");
+      }
+    }
+    off += n;
+  }
+  r = ncclGroupEnd();
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+  return MMCL_OK;
+}
+
+int mmcl_all_reduce_sum_f32(mmcl_handle* h, float* buf, int64_t n, mmcl_stream stream) {
+  REQUIRE(h && (n == 0 || buf), "mmcl_all_reduce_sum_f32: bad arguments");
+  if (h->world == 1 || n == 0) return MMCL_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  ncclResult_t r = ncclAllReduce(buf, buf, size_t(n), ncclFloat, ncclSum, h->comm,
+                                 static_cast<cudaStream_t>(stream));
+  if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+  return MMCL_OK;
+}
+
+size_t mmcl_sim_lse_workspace_bytes(mmcl_handle* h, int64_t nq, int64_t nk, int64_t d) {
+  if (!h || nq <= 0 || nk <= 0 || d <= 0) return 0;
+  return sim_lse_workspace_bytes(h->num_sms, nq, nk, d);
+}
+
+static int check_sim_args(const char* fn, const void* a, int64_t na, const void* b, int64_t nb,
+                          int64_t d) {
+  if (na < 0 || nb < 0) return fail(MMCL_ERR_INVALID, std::string(fn) + ": negative size");
+  if (d <= 0 || d % 8 != 0 || d > 2048)
+    return fail(MMCL_ERR_INVALID, std::string(fn) + ": d must be a multiple of 8 in [8, 2048]");
+  if (na >= (1ll << 31) || nb >= (1ll << 31))
+    return fail(MMCL_ERR_INVALID, std::string(fn) + ": more than 2^31 rows");
+  if ((na > 0 && !a) || (nb > 0 && !b)) return fail(MMCL_ERR_INVALID, std::string(fn) + ": null matrix");
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
+    return fail(MMCL_ERR_INVALID, std::string(fn) + ": matrices must be 16-byte aligned");
+  return MMCL_OK;
+}
+
+int mmcl_sim_lse_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                     int64_t nk, int64_t d, const float* scale, float* lse, float* esum,
+                     void* workspace, size_t workspace_bytes, mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_sim_lse_fwd: null handle/scale");
+  int rc = check_sim_args("mmcl_sim_lse_fwd", q_bf16, nq, k_bf16, nk, d);
+  if (rc) return rc;
+  if (nq == 0) return MMCL_OK;
+  REQUIRE(nk > 0, "mmcl_sim_lse_fwd: nk must be positive (log-sum-exp over an empty set)");
+  REQUIRE(lse, "mmcl_sim_lse_fwd: null lse");
+  if (workspace_bytes < sim_lse_workspace_bytes(h->num_sms, nq, nk, d) || !workspace)
+    return fail(MMCL_ERR_WORKSPACE, "mmcl_sim_lse_fwd: workspace too small");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const char* err = nullptr;
+  cudaError_t e = launch_sim_lse_fwd(h->num_sms, q_bf16, nq, k_bf16, nk, d, scale, lse, esum,
+                                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream),
+                                     &err);
+  if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_lse_fwd");
+  return MMCL_OK;
+}
+
+int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                         int64_t nk, int64_t d, int64_t label_offset, const float* scale,
+                         float* pos, mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_positive_logits: null handle/scale");
+  int rc = check_sim_args("mmcl_positive_logits", q_bf16, nq, k_bf16, nk, d);
+  if (rc) return rc;
+  REQUIRE(nq == 0 || pos, "mmcl_positive_logits: null pos");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_positive_logits(q_bf16, nq, k_bf16, nk, d, label_offset, scale, pos,
+                                         static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_positive_logits");
+}
+
+int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const float* esum_a,
+                   const float* esum_b, const float* pos, int64_t n, double weight, double n_norm,
+                   const float* scale, float* out2, mmcl_stream stream) {
+  REQUIRE(h && scale && out2, "mmcl_pair_loss: null handle/scale/out");
+  REQUIRE(n >= 0 && n_norm > 0, "mmcl_pair_loss: bad n / n_norm");
+  REQUIRE(n == 0 || (lse_a && lse_b && esum_a && esum_b && pos), "mmcl_pair_loss: null vector");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_pair_loss(lse_a, lse_b, esum_a, esum_b, pos, n, weight, n_norm, scale,
+                                   out2, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_pair_loss");
+}
+
+int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16,
+                      int64_t ny, int64_t d, const float* scale, const float* off_row,
+                      const float* off_col, float* dx, mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_sim_grad_bwd: null handle/scale");
+  int rc = check_sim_args("mmcl_sim_grad_bwd", x_bf16, nx, y_bf16, ny, d);
+  if (rc) return rc;
+  if (nx == 0 || ny == 0) return MMCL_OK;
+  REQUIRE(dx, "mmcl_sim_grad_bwd: null dx");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const char* err = nullptr;
+  cudaError_t e = launch_sim_grad_bwd(h->num_sms, x_bf16, nx, y_bf16, ny, d, scale, off_row,
+                                      off_col, dx, static_cast<cudaStream_t>(stream), &err);
+  if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_grad_bwd");
+  return MMCL_OK;
+}
+
+int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* denom_vec,
+                      double denom_scalar, float* off, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_make_offsets: null handle");
+  REQUIRE(n >= 0 && (n == 0 || (lse && off)), "mmcl_make_offsets: bad arguments");
+  REQUIRE(denom_vec || denom_scalar > 0, "mmcl_make_offsets: denominator must be positive");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_make_offsets(lse, n, denom_vec, denom_scalar, off,
+                                      static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_make_offsets");
+}
+
+int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16, int64_t n,
+                     int64_t d, double weight, double pos_coef, const float* gout,
+                     const float* scale, const void* src, int src_dtype, const float* inv_norm,
+                     int normalize, const int64_t* idx, float* grad_f32, mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_unpack_grad: null handle/scale");
+  REQUIRE(n >= 0 && d > 0 && d % 8 == 0 && d <= 2048, "mmcl_unpack_grad: bad n/d");
+  REQUIRE(src_dtype >= 0 && src_dtype <= 2, "mmcl_unpack_grad: dtype must be f32/bf16/f16");
+  REQUIRE(n == 0 || (dacc && partner_bf16 && grad_f32), "mmcl_unpack_grad: null buffer");
+  REQUIRE(!normalize || (src && inv_norm), "mmcl_unpack_grad: normalize needs src and inv_norm");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_unpack_grad(dacc, partner_bf16, n, d, weight, pos_coef, gout, scale, src,
+                                     src_dtype, inv_norm, normalize, idx, grad_f32,
+                                     static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_unpack_grad");
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// HBM-bound helper kernels around the two tensor-core kernels: row packing (select + L2
+// normalise + bf16 cast), positive logits, loss assembly, offset vectors, gradient unpack
+// (positive-label term, normalise backward, scatter-add).  One warp per embedding row,
+// 16-byte vector accesses.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "kernels.h"
+
+namespace mmcl {
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// load 8 consecutive elements (d % 8 == 0, rows 16-byte aligned) as fp32
+template <int DT>
+__device__ __forceinline__ void load8(const void* base, long long elem, float (&f)[8]) {
+  if (DT == 0) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else if (DT == 1) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + elem));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(base) + elem));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      const float2 t = __half22float2(h);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int DT>
+__global__ void pack_rows_kernel(const void* __restrict__ src, long long src_rows, int d,
+                                 const int64_t* __restrict__ idx, long long n_out, int normalize,
+                                 __nv_bfloat16* __restrict__ dst, float* __restrict__ inv_norm) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_out) return;
+  long long srow = idx ? idx[row] : row;
+  if (srow < 0 || srow >= src_rows) srow = 0;  // defensive; the matcher only emits valid rows
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int c = lane * 8; c < d; c += 256) {
+      float f[8];
+      load8<DT>(src, srow * d + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+    }
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+  }
+  for (int c = lane * 8; c < d; c += 256) {
+    float f[8];
+    load8<DT>(src, srow * d + c, f);
+    uint4 o;
+    o.x = bf16x2(f[0] * inv, f[1] * inv);
+    o.y = bf16x2(f[2] * inv, f[3] * inv);
+    o.z = bf16x2(f[4] * inv, f[5] * inv);
+    o.w = bf16x2(f[6] * inv, f[7] * inv);
+    *reinterpret_cast<uint4*>(dst + row * d + c) = o;
+  }
+  if (inv_norm && lane == 0) inv_norm[row] = inv;
+}
+
+__global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long long nq,
+                                       const __nv_bfloat16* __restrict__ k, long long nk, int d,
+                                       long long label_offset, const float* __restrict__ scale,
+                                       float* __restrict__ pos) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  const long long krow = label_offset + row;
+  float acc = 0.f;
+  if (krow >= 0 && krow < nk) {
+    for (int c = lane * 8; c < d; c += 256) {
+      float a[8], b[8];
+      load8<1>(q, row * d + c, a);
+      load8<1>(k, krow * d + c, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) pos[row] = acc * (*scale);
+}
+
+__global__ void pair_loss_kernel(const float* __restrict__ lse_a, const float* __restrict__ lse_b,
+                                 const float* __restrict__ esum_a, const float* __restrict__ esum_b,
+                                 const float* __restrict__ pos, long long n, double coef,
+                                 const float* __restrict__ scale, float* __restrict__ out2) {
+  __shared__ double sh[2][32];
+  double l = 0.0, e = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double p2 = 2.0 * (double)pos[i];
+    l += (double)lse_a[i] + (double)lse_b[i] - p2;
+    e += (double)esum_a[i] + (double)esum_b[i] - p2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][w] = l; sh[1][w] = e; }
+  __syncthreads();
+  if (w == 0) {
+    l = lane < (blockDim.x >> 5) ? sh[0][lane] : 0.0;
+    e = lane < (blockDim.x >> 5) ? sh[1][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    if (lane == 0) {
+      out2[0] += (float)(coef * l);
+      out2[1] += (float)(coef * e / (double)(*scale));
+    }
+  }
+}
+
+__global__ void make_offsets_kernel(const float* __restrict__ lse, long long n,
+                                    const float* __restrict__ denom_vec, float denom_log2,
+                                    float* __restrict__ off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dl = denom_vec ? log2f(denom_vec[i]) : denom_log2;
+  off[i] = fmaf(lse[i], LOG2E, dl);
+}
+
+template <int DT>
+__global__ void unpack_grad_kernel(const float* __restrict__ dacc,
+                                   const __nv_bfloat16* __restrict__ partner, long long n, int d,
+                                   float weight, float pos_coef, const float* __restrict__ gout,
+                                   const float* __restrict__ scale, const void* __restrict__ src,
+                                   const float* __restrict__ inv_norm, int normalize,
+                                   const int64_t* __restrict__ idx, float* __restrict__ grad) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float coef = weight * (gout ? *gout : 1.f) * (*scale);
+  const long long srow = idx ? idx[row] : row;
+  constexpr int MAXV = 8;  // supports d <= 2048 with the register-resident path
+  float g[MAXV][8];
+  float dot = 0.f;
+  const float inv = normalize ? inv_norm[row] : 1.f;
+  int nv = 0;
+  for (int c = lane * 8; c < d; c += 256, ++nv) {
+    float pa[8];
+    const float4 a0 = *reinterpret_cast<const float4*>(dacc + row * d + c);
+    const float4 a1 = *reinterpret_cast<const float4*>(dacc + row * d + c + 4);
+    load8<1>(partner, row * d + c, pa);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pos_coef * pa[i]);
+    if (normalize) {
+      float x[8];
+      load8<DT>(src, srow * d + c, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[i] * inv, dot);
+    }
+  }
+  if (normalize) dot = warp_sum(dot);
+  const bool clamped = inv >= 0.99e12f;  // ||x|| < eps: x_hat = x / eps, a plain scaling
+  nv = 0;
+  for (int c = lane * 8; c < d; c += 256, ++nv) {
+    float o[8];
+    if (normalize) {
+      float x[8];
+      load8<DT>(src, srow * d + c, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = clamped ? g[nv][i] * inv : inv * (g[nv][i] - x[i] * inv * dot);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = g[nv][i];
+    }
+    float* dst = grad + srow * d + c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, o[i]);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows, long long d,
+                             const int64_t* idx, long long n_out, int normalize, void* dst_bf16,
+                             float* inv_norm, cudaStream_t stream) {
+  if (n_out == 0) return cudaSuccess;
+  const int wpb = 8;
+  const unsigned blocks = unsigned((n_out + wpb - 1) / wpb);
+  auto* dst = static_cast<__nv_bfloat16*>(dst_bf16);
+  if (src_dtype == 0)
+    pack_rows_kernel<0><<<blocks, wpb * 32, 0, stream>>>(src, src_rows, int(d), idx, n_out, normalize, dst, inv_norm);
+  else if (src_dtype == 1)
+    pack_rows_kernel<1><<<blocks, wpb * 32, 0, stream>>>(src, src_rows, int(d), idx, n_out, normalize, dst, inv_norm);
+  else
+    pack_rows_kernel<2><<<blocks, wpb * 32, 0, stream>>>(src, src_rows, int(d), idx, n_out, normalize, dst, inv_norm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, long long nk,
+                                   long long d, long long label_offset, const float* scale,
+                                   float* pos, cudaStream_t stream) {
+  if (nq == 0) return cudaSuccess;
+  const int wpb = 8;
+  positive_logits_kernel<<<unsigned((nq + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(q), nq, static_cast<const __nv_bfloat16*>(k), nk, int(d),
+      label_offset, scale, pos);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_loss(const float* lse_a, const float* lse_b, const float* esum_a,
+                             const float* esum_b, const float* pos, long long n, double weight,
+                             double n_norm, const float* scale, float* out2, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  pair_loss_kernel<<<1, 1024, 0, stream>>>(lse_a, lse_b, esum_a, esum_b, pos, n,
+                                           weight / (2.0 * n_norm), scale, out2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_make_offsets(const float* lse, long long n, const float* denom_vec,
+                                double denom_scalar, float* off, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  make_offsets_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+      lse, n, denom_vec, denom_vec ? 0.f : (float)log2(denom_scalar), off);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16, long long n,
+                               long long d, double weight, double pos_coef, const float* gout,
+                               const float* scale, const void* src, int src_dtype,
+                               const float* inv_norm, int normalize, const int64_t* idx,
+                               float* grad_f32, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int wpb = 4;
+  const unsigned blocks = unsigned((n + wpb - 1) / wpb);
+  auto* pb = static_cast<const __nv_bfloat16*>(partner_bf16);
+  if (src_dtype == 0)
+    unpack_grad_kernel<0><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+  else if (src_dtype == 1)
+    unpack_grad_kernel<1><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+  else
+    unpack_grad_kernel<2><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+  return cudaGetLastError();
+}
+
+}  // namespace mmcl

@@ -1,0 +1,46 @@
+// Internal launcher declarations shared by the .cu files and api.cu (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace mmcl {
+
+// sim_fwd.cu
+size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d);
+cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const void* k,
+                               long long nk, long long d, const float* scale, float* lse,
+                               float* esum, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream, const char** err);
+
+// sim_bwd.cu
+cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
+                                long long ny, long long d, const float* scale,
+                                const float* off_row, const float* off_col, float* dx,
+                                cudaStream_t stream, const char** err);
+
+// aux_kernels.cu
+cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows, long long d,
+                             const int64_t* idx, long long n_out, int normalize, void* dst_bf16,
+                             float* inv_norm, cudaStream_t stream);
+cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, long long nk,
+                                   long long d, long long label_offset, const float* scale,
+                                   float* pos, cudaStream_t stream);
+cudaError_t launch_pair_loss(const float* lse_a, const float* lse_b, const float* esum_a,
+                             const float* esum_b, const float* pos, long long n, double weight,
+                             double n_norm, const float* scale, float* out2, cudaStream_t stream);
+cudaError_t launch_make_offsets(const float* lse, long long n, const float* denom_vec,
+                                double denom_scalar, float* off, cudaStream_t stream);
+cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16, long long n,
+                               long long d, double weight, double pos_coef, const float* gout,
+                               const float* scale, const void* src, int src_dtype,
+                               const float* inv_norm, int normalize, const int64_t* idx,
+                               float* grad_f32, cudaStream_t stream);
+
+// match.cu
+size_t match_workspace_bytes(long long n, long long m);
+cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* ids_b, long long m,
+                             int64_t* out_a, int64_t* out_b, long long capacity, int64_t* out_info,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace mmcl

@@ -1,0 +1,351 @@
+// Forward hot kernel: S = s * Q K^T in 128x256 fp32 tiles that live only in tensor memory,
+// reduced on the fly to per-row (max, sum-exp, sum-exp*logit).
+//
+// Roles (256 threads, 1 CTA / SM, persistent):
+//   warp 0    TMA producer  (Q tile resident in smem when it fits, K streamed in 64-wide k-chunks)
+//   warp 1    tcgen05.mma issuer (one elected thread), double-buffered TMEM accumulators
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> online log-sum-exp in registers (one row per thread)
+// Work distribution: the nqt x nkt tile grid is linearised (q-tile major) and cut into
+// equal contiguous ranges, one per CTA ("stream-K" over the key axis), so all 148 SMs finish
+// together whatever nq is; a row's partial statistics from different CTAs are merged by
+// lse_combine_kernel.
+#include "kernels.h"
+#include "tma_host.h"
+#include "umma.cuh"
+
+namespace mmcl {
+
+namespace {
+
+constexpr int BM = 128;      // query rows per tile (UMMA M)
+constexpr int BN = 256;      // key rows per tile (UMMA N); N=256 is the only shape that amortises
+                             // the ~128-cycle per-instruction floor measured in tools/umma_rate*.cu
+constexpr int BK = 64;       // k-chunk: 64 bf16 = one 128-byte swizzle atom
+constexpr int QCHUNK_BYTES = BM * BK * 2;  // 16 KB
+constexpr int KCHUNK_BYTES = BN * BK * 2;  // 32 KB
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct FwdParams {
+  int nq, nk, kchunks;
+  int nqt, nkt;
+  long long total_tiles;
+  int tiles_per_cta;
+  int nstages;
+  int max_slots;
+  long long part_stride;  // floats between slots (= nqt * BM)
+  const float* scale;
+  float* part_m;
+  float* part_l;
+  float* part_t;
+};
+
+template <bool kQRes>
+__global__ void __launch_bounds__(256, 1)
+sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
+  const int stage_bytes = kQRes ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
+  uint8_t* sQ = smem;
+  uint8_t* sStage = smem + (kQRes ? p.kchunks * QCHUNK_BYTES : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.nstages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.nstages;
+  uint64_t* q_full = bars + 2 * p.nstages;
+  uint64_t* q_empty = q_full + 1;
+  uint64_t* acc_full = q_full + 2;   // [2]
+  uint64_t* acc_empty = q_full + 4;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    for (int i = 0; i < p.nstages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long t_begin = (long long)blockIdx.x * p.tiles_per_cta;
+  long long t_end = t_begin + p.tiles_per_cta;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      for (long long t = t_begin; t < t_end;) {
+        const int qt = int(t / p.nkt), kt0 = int(t % p.nkt);
+        int kt1 = kt0 + int(t_end - t);
+        if (kt1 > p.nkt) kt1 = p.nkt;
+        if (kQRes) {
+          mbar_wait(q_empty, qphase ^ 1);
+          mbar_arrive_expect_tx(q_full, p.kchunks * QCHUNK_BYTES);
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_2d(sQ + kc * QCHUNK_BYTES, &tmQ, kc * BK, qt * BM, q_full);
+          qphase ^= 1;
+        }
+        for (int kt = kt0; kt < kt1; ++kt) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], stage_bytes);
+            uint8_t* dst = sStage + stage * stage_bytes;
+            if (!kQRes) {
+              tma_load_2d(dst, &tmQ, kc * BK, qt * BM, &full[stage]);
+              dst += QCHUNK_BYTES;
+            }
+            tma_load_2d(dst, &tmK, kc * BK, kt * BN, &full[stage]);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+        t += kt1 - kt0;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      uint32_t acc = 0;
+      for (long long t = t_begin; t < t_end;) {
+        const int kt0 = int(t % p.nkt);
+        int kt1 = kt0 + int(t_end - t);
+        if (kt1 > p.nkt) kt1 = p.nkt;
+        if (kQRes) {
+          mbar_wait(q_full, qphase);
+          qphase ^= 1;
+        }
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
+          mbar_wait(&acc_empty[ab], aphase ^ 1);
+          tc_fence_after();
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(sStage + stage * stage_bytes);
+            const uint32_t qa = kQRes ? smem_u32(sQ + kc * QCHUNK_BYTES) : st;
+            const uint32_t ka = kQRes ? st : st + QCHUNK_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(qa + k * 32, 0, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(ka + k * 32, 0, 1024);
+              umma_ss(tmem + ab * BN, adesc, bdesc, idesc, (kc | k) != 0);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[ab]);
+          ++acc;
+        }
+        if (kQRes) umma_commit(q_empty);
+        t += kt1 - kt0;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp - 4;  // == warp % 4: TMEM lane quadrant
+    const int row = q * 32 + lane;
+    const float s = *p.scale;
+    const float c = s * LOG2E;
+    const bool neg = c < 0.f;
+    uint32_t acc = 0;
+    for (long long t = t_begin; t < t_end;) {
+      const int qt = int(t / p.nkt), kt0 = int(t % p.nkt);
+      int kt1 = kt0 + int(t_end - t);
+      if (kt1 > p.nkt) kt1 = p.nkt;
+      float m = -INFINITY, l = 0.f, tt = 0.f;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
+        mbar_wait(&acc_full[ab], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
+        const int valid = p.nk - kt * BN;  // columns of this tile that exist (>= 1)
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == BN / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+          }
+          const int cv = valid - ch * 32;
+          if (cv >= 32) {
+            float ext = __uint_as_float(v[0]);
+            if (!neg) {
+#pragma unroll
+              for (int e = 1; e < 32; ++e) ext = fmaxf(ext, __uint_as_float(v[e]));
+            } else {
+#pragma unroll
+              for (int e = 1; e < 32; ++e) ext = fminf(ext, __uint_as_float(v[e]));
+            }
+            const float mn = fmaxf(m, ext * c);
+            const float alpha = ex2f(m - mn);
+            l *= alpha;
+            tt *= alpha;
+            m = mn;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = __uint_as_float(v[e]);
+              const float pe = ex2f(fmaf(x, c, -m));
+              l += pe;
+              tt = fmaf(pe, x, tt);
+            }
+          } else if (cv > 0) {
+            // ragged last tile: only the first cv columns exist
+            float ext = neg ? INFINITY : -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = __uint_as_float(v[e]);
+              if (e < cv) ext = neg ? fminf(ext, x) : fmaxf(ext, x);
+            }
+            const float mn = fmaxf(m, ext * c);
+            const float alpha = ex2f(m - mn);
+            l *= alpha;
+            tt *= alpha;
+            m = mn;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = __uint_as_float(v[e]);
+              if (e < cv) {
+                const float pe = ex2f(fmaf(x, c, -m));
+                l += pe;
+                tt = fmaf(pe, x, tt);
+              }
+            }
+          }
+        }
+        ++acc;
+      }
+      // partial statistics of this (q-tile, key range) segment
+      const long long first_tile = (long long)qt * p.nkt;
+      const int c_first = int(first_tile / p.tiles_per_cta);
+      const int slot = int(blockIdx.x) - c_first;
+      const long long o = (long long)slot * p.part_stride + (long long)qt * BM + row;
+      p.part_m[o] = m;
+      p.part_l[o] = l;
+      p.part_t[o] = tt;
+      t += kt1 - kt0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// Merge the per-CTA partial statistics of each row.
+__global__ void lse_combine_kernel(FwdParams p, float* __restrict__ lse, float* __restrict__ esum) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.nq) return;
+  const int qt = row / BM;
+  const long long first_tile = (long long)qt * p.nkt;
+  const int c_first = int(first_tile / p.tiles_per_cta);
+  const int c_last = int((first_tile + p.nkt - 1) / p.tiles_per_cta);
+  float M = -INFINITY;
+  for (int s = 0; s <= c_last - c_first; ++s)
+    M = fmaxf(M, p.part_m[(long long)s * p.part_stride + row]);
+  float L = 0.f, T = 0.f;
+  for (int s = 0; s <= c_last - c_first; ++s) {
+    const long long o = (long long)s * p.part_stride + row;
+    const float w = exp2f(p.part_m[o] - M);
+    L += p.part_l[o] * w;
+    T += p.part_t[o] * w;
+  }
+  const float sc = *p.scale;
+  lse[row] = (M + log2f(L)) * LN2;
+  if (esum) esum[row] = sc * T / L;
+}
+
+int fwd_plan(int num_sms, long long nq, long long nk, long long d, FwdParams* p, bool* qres,
+             size_t* smem_bytes) {
+  p->nq = int(nq);
+  p->nk = int(nk);
+  p->kchunks = int((d + BK - 1) / BK);
+  p->nqt = int((nq + BM - 1) / BM);
+  p->nkt = int((nk + BN - 1) / BN);
+  p->total_tiles = (long long)p->nqt * p->nkt;
+  long long ctas = p->total_tiles < num_sms ? p->total_tiles : num_sms;
+  p->tiles_per_cta = int((p->total_tiles + ctas - 1) / ctas);
+  p->max_slots = (p->nkt + p->tiles_per_cta - 1) / p->tiles_per_cta + 1;
+  p->part_stride = (long long)p->nqt * BM;
+  const size_t budget = 227 * 1024 - 256 /*barriers*/;
+  *qres = size_t(p->kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= budget;
+  const size_t stage_bytes = *qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
+  const size_t fixed = *qres ? size_t(p->kchunks) * QCHUNK_BYTES : 0;
+  int ns = int((budget - fixed) / stage_bytes);
+  if (ns > 8) ns = 8;
+  p->nstages = ns;
+  *smem_bytes = fixed + ns * stage_bytes + 256;
+  return 0;
+}
+
+}  // namespace
+
+size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d) {
+  FwdParams p;
+  bool qres;
+  size_t smem;
+  fwd_plan(num_sms, nq, nk, d, &p, &qres, &smem);
+  return size_t(3) * p.max_slots * p.part_stride * sizeof(float);
+}
+
+cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const void* k,
+                               long long nk, long long d, const float* scale, float* lse,
+                               float* esum, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream, const char** err) {
+  FwdParams p;
+  bool qres;
+  size_t smem;
+  fwd_plan(num_sms, nq, nk, d, &p, &qres, &smem);
+  const size_t need = size_t(3) * p.max_slots * p.part_stride * sizeof(float);
+  if (workspace_bytes < need) {
+    *err = "sim_lse_fwd: workspace too small";
+    return cudaErrorInvalidValue;
+  }
+  p.scale = scale;
+  p.part_m = static_cast<float*>(workspace);
+  p.part_l = p.part_m + size_t(p.max_slots) * p.part_stride;
+  p.part_t = p.part_l + size_t(p.max_slots) * p.part_stride;
+  CUtensorMap tmQ, tmK;
+  if (make_tmap_bf16_sw128(&tmQ, q, nq, d, d, BM) || make_tmap_bf16_sw128(&tmK, k, nk, d, d, BN)) {
+    *err = "sim_lse_fwd: cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  const int ctas = int((p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
+  cudaError_t e;
+  if (qres) {
+    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(smem));
+    if (e != cudaSuccess) return e;
+    sim_lse_fwd_kernel<true><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
+  } else {
+    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    sim_lse_fwd_kernel<false><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  lse_combine_kernel<<<(p.nq + 255) / 256, 256, 0, stream>>>(p, lse, esum);
+  return cudaGetLastError();
+}
+
+}  // namespace mmcl

@@ -1,0 +1,532 @@
+"""B200-native drop-in for ``mmlearn.modules.losses.ContrastiveLoss``.
+
+Same constructor flags and ``forward(embeddings, example_ids, logit_scale, modality_loss_pairs)``
+signature as the reference (mmlearn/modules/losses/contrastive.py:40-65); behind it, PyTorch only
+allocates buffers and provides the stream and ``torch.distributed`` plumbing, and every piece of
+arithmetic runs in ``libmmcl.so`` (hand-written sm_100a kernels, ``include/mmcl.h``).
+
+Formulation.  For a pair (a, b) with matched, normalised rows A, B and
+S = s * A_all B_all^T, rank r owns row block [off_r, off_r + b_r) of S.  Direction-a logits of the
+rank are that row block; direction-b logits are the matching *column* block (S is shared by both
+directions because the matched global order is the concatenation of the local orders -- checked
+at run time).  Forward: two row-wise fused GEMM+LSE passes (A_r x B_all, B_r x A_all).  Backward:
+the same two products are recomputed tile by tile with
+    G[i,j] = softmax_row(S)[i,j]/den_row + softmax_col(S)[i,j]/den_col(j)
+folded into the epilogue, which yields dA_r and dB_r complete on the owning rank: only the [N]
+log-sum-exp vectors cross NVLink in backward, never an [N,d] gradient.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib
+from ._lib import check, counts_array, ptr
+from .modalities import LossPairSpec, Modalities
+from .plan import PairPlan, all_gather_ints, dist_info
+
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_HANDLES: dict = {}
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def get_handle(device: torch.device):
+    """One mmcl handle per (device, world).  For world > 1 rank 0 creates the NCCL unique id and
+    it is broadcast through the caller's torch.distributed group."""
+    import ctypes
+
+    world, rank = dist_info()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), world)
+    h = _HANDLES.get(key)
+    if h is not None:
+        return h
+    lib = _lib.load()
+    uid = None
+    if world > 1:
+        buf = ctypes.create_string_buffer(_lib.NCCL_UID_BYTES)
+        if rank == 0:
+            check(lib.mmcl_nccl_unique_id(buf), "mmcl_nccl_unique_id")
+        obj = [bytes(buf.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        uid = ctypes.create_string_buffer(obj[0], _lib.NCCL_UID_BYTES)
+    out = ctypes.c_void_p()
+    check(lib.mmcl_create(ctypes.byref(out), key[0], rank, world, uid), "mmcl_create")
+    _HANDLES[key] = out
+    return out
+
+
+def _validate_ids(first, second) -> None:
+    """Error behaviour of mmlearn/datasets/core/example.py:140-157."""
+    if not isinstance(first, torch.Tensor) or not isinstance(second, torch.Tensor):
+        raise TypeError(
+            f"Expected inputs to be tensors, but got {type(first)} and {type(second)}."
+        )
+    if not (first.ndim == 2 and first.shape[1] == 2):
+        raise ValueError(
+            "Expected argument `first_example_ids` to be a tensor of shape (N, 2), "
+            f"but got shape {first.shape}."
+        )
+    if not (second.ndim == 2 and second.shape[1] == 2):
+        raise ValueError(
+            "Expected argument `second_example_ids` to be a tensor of shape (N, 2), "
+            f"but got shape {second.shape}."
+        )
+
+
+class _Match:
+    """An in-flight device id match; ``info`` = [k, identity] (device int64)."""
+
+    def __init__(self, h, ids_a: torch.Tensor, ids_b: torch.Tensor, capacity: Optional[int] = None):
+        lib = _lib.load()
+        self.h, self.ids_a, self.ids_b = h, ids_a, ids_b
+        dev = ids_a.device
+        n, m = ids_a.shape[0], ids_b.shape[0]
+        self.capacity = max(n, m, 1) if capacity is None else capacity
+        self.out_a = torch.empty(self.capacity, dtype=torch.long, device=dev)
+        self.out_b = torch.empty(self.capacity, dtype=torch.long, device=dev)
+        self.info = torch.empty(2, dtype=torch.long, device=dev)
+        ws_bytes = lib.mmcl_match_workspace_bytes(n, m)
+        self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        check(lib.mmcl_match_ids(h, ptr(ids_a), n, ptr(ids_b), m, ptr(self.out_a), ptr(self.out_b),
+                                 self.capacity, ptr(self.info), ptr(self.ws), self.ws.numel(),
+                                 _stream(dev)), "mmcl_match_ids")
+
+    def finish(self, k: int):
+        """Index tensors once the host knows k (re-runs with a larger buffer on overflow)."""
+        if k > self.capacity:
+            again = _Match(self.h, self.ids_a, self.ids_b, capacity=k)
+            return again.out_a[:k], again.out_b[:k]
+        return self.out_a[:k], self.out_b[:k]
+
+
+def find_matching_indices(first_example_ids: torch.Tensor, second_example_ids: torch.Tensor):
+    """Device version of ``mmlearn.datasets.core.find_matching_indices``
+    (mmlearn/datasets/core/example.py:101-166): same order, same errors."""
+    _validate_ids(first_example_ids, second_example_ids)
+    if not first_example_ids.is_cuda:
+        raise ValueError("mmlearn_b200.find_matching_indices needs CUDA tensors (no CPU fallback)")
+    a = first_example_ids.to(torch.long).contiguous()
+    b = second_example_ids.to(device=a.device, dtype=torch.long).contiguous()
+    m = _Match(get_handle(a.device), a, b)
+    k = int(m.info[0].item())
+    return m.finish(k)
+
+
+class _PairState:
+    """Everything one modality pair needs between forward and backward."""
+
+    __slots__ = ("plan", "key_a", "key_b", "idx_a", "idx_b", "fa_all", "fb_all", "inv_a", "inv_b",
+                 "lse_a", "lse_b", "lse_a_all", "lse_b_all", "scale_index", "pos")
+
+
+class _FusedContrastiveFn(torch.autograd.Function):
+    """loss = f(logit_scale, *embeddings); all other state travels in ``ctx.run``."""
+
+    @staticmethod
+    def forward(ctx, run, logit_scale, *embs):
+        loss, dscale = run.forward(logit_scale, embs)
+        ctx.run = run
+        ctx.save_for_backward(dscale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dscale,) = ctx.saved_tensors
+        run = ctx.run
+        grads = run.backward(gout)
+        gs = None
+        if ctx.needs_input_grad[1]:
+            gs = (dscale * gout).to(run.scale_dtype)
+            gs = gs.reshape(run.scale_shape) if run.scale_shape != gs.shape else gs
+        return (None, gs, *grads)
+
+
+class _Run:
+    """One forward(+backward) evaluation of the loss."""
+
+    def __init__(self, module, keys, example_ids, pairs):
+        self.m = module
+        self.keys = keys  # embedding dict keys, in the order the tensors are passed
+        self.example_ids = example_ids
+        self.pairs = pairs
+        self.states: list[_PairState] = []
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, logit_scale: torch.Tensor, embs):
+        lib = _lib.load()
+        m = self.m
+        world, rank = dist_info()
+        dev = embs[0].device
+        h = get_handle(dev)
+        st = _stream(dev)
+        self.dev, self.h = dev, h
+        self.embs = dict(zip(self.keys, embs))
+        self.scale_shape, self.scale_dtype = logit_scale.shape, logit_scale.dtype
+        P = len(self.pairs)
+        scale = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if scale.numel() not in (1, P):
+            raise ValueError(
+                f"logit_scale must be a scalar or have one entry per modality pair ({P}), got "
+                f"shape {tuple(logit_scale.shape)}")
+        self.scale = scale
+        d = embs[0].shape[-1]
+
+        # ---- 1. local id matching (contrastive.py:268-291), all pairs in flight at once ----
+        ids = {}
+
+        def ids_of(name):
+            if name not in ids:
+                t = self.example_ids[name]
+                ids[name] = t.to(device=dev, dtype=torch.long).contiguous()
+            return ids[name]
+
+        matches: list[Optional[_Match]] = []
+        mods = []
+        for pair in self.pairs:
+            ma = Modalities.get_modality(pair.modalities[0])
+            mb = Modalities.get_modality(pair.modalities[1])
+            mods.append((ma, mb))
+            if ma.embedding in self.embs and mb.embedding in self.embs:
+                _validate_ids(self.example_ids[ma.name], self.example_ids[mb.name])
+                matches.append(_Match(h, ids_of(ma.name), ids_of(mb.name)))
+            else:
+                matches.append(None)
+        info = torch.zeros(P, 2, dtype=torch.long, device=dev)
+        for p, mt in enumerate(matches):
+            if mt is not None:
+                info[p] = mt.info
+        # one exchange: [k, identity] per pair from every rank (replaces contrastive.py:197-206
+        # and the shape gathers of _gather_all_tensors)
+        all_info = all_gather_ints(info.view(-1), world).view(world, P, 2).cpu()  # host sync
+
+        # ---- 2. per pair: pack matched rows straight into the gather buffer, all-gather ----
+        out2 = torch.zeros(P, 2, dtype=torch.float32, device=dev)
+        need_grad = torch.is_grad_enabled() and (
+            any(e.requires_grad for e in embs) or logit_scale.requires_grad)
+        shared: dict = {}
+        losses_present = False
+        for p, pair in enumerate(self.pairs):
+            ma, mb = mods[p]
+            counts = [int(all_info[r, p, 0]) for r in range(world)]
+            n_total = sum(counts)
+            if n_total == 0:
+                continue  # nobody has this pair: every rank skips it (contrastive.py:304-316)
+            plan = PairPlan(counts=counts, rank=rank, local_loss=m.local_loss,
+                            gather_with_grad=m.gather_with_grad, weight=float(pair.weight))
+            stt = _PairState()
+            stt.plan, stt.key_a, stt.key_b = plan, ma.embedding, mb.embedding
+            stt.scale_index = p if scale.numel() > 1 else 0
+            k = plan.b_local
+            ident = bool(all_info[rank, p, 1]) and k > 0
+            if k > 0:
+                ia, ib = matches[p].finish(k)
+                stt.idx_a, stt.idx_b = (None, None) if ident else (ia, ib)
+            else:
+                stt.idx_a = stt.idx_b = None
+            all_ident = all(bool(all_info[r, p, 1]) or counts[r] == 0 for r in range(world))
+            if world > 1:
+                self._check_global_order(ma, mb, ids_of, counts, world)
+
+            def gathered(key, idx, name):
+                ck = (key, "identity") if all_ident else None
+                if ck is not None and ck in shared:
+                    return shared[ck]
+                src = self.embs[key] if key in self.embs else None
+                f_all = torch.empty(n_total, d, dtype=torch.bfloat16, device=dev)
+                inv = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
+                if k > 0:
+                    s_c = src.detach().contiguous()
+                    if s_c.dtype not in _DTYPES:
+                        raise ValueError(f"unsupported embedding dtype {s_c.dtype}")
+                    check(lib.mmcl_pack_rows(h, ptr(s_c), _DTYPES[s_c.dtype], s_c.shape[0], d,
+                                             ptr(idx), k, int(m.l2_normalize),
+                                             f_all.data_ptr() + plan.offset * d * 2, ptr(inv), st),
+                          "mmcl_pack_rows")
+                if world > 1:
+                    check(lib.mmcl_all_gather_rows(h, f_all.data_ptr() + plan.offset * d * 2,
+                                                   ptr(f_all), counts_array(counts), d * 2, st),
+                          "mmcl_all_gather_rows")
+                if ck is not None:
+                    shared[ck] = (f_all, inv)
+                return f_all, inv
+
+            stt.fa_all, stt.inv_a = gathered(ma.embedding, stt.idx_a, ma.name)
+            stt.fb_all, stt.inv_b = gathered(mb.embedding, stt.idx_b, mb.name)
+            self.states.append(stt)
+            if m.cache_labels:
+                m._remember_labels(plan, dev)
+            if k == 0:
+                continue  # skipped process: contributes keys only (contrastive.py:283-301)
+            losses_present = True
+
+            # ---- 3. fused similarity + log-sum-exp, both directions ----
+            off = plan.offset
+            fa = stt.fa_all[off:off + k]
+            fb = stt.fb_all[off:off + k]
+            sp = scale.data_ptr() + 4 * stt.scale_index
+            lse_a = torch.empty(k, dtype=torch.float32, device=dev)
+            lse_b = torch.empty(k, dtype=torch.float32, device=dev)
+            es_a = torch.empty(k, dtype=torch.float32, device=dev)
+            es_b = torch.empty(k, dtype=torch.float32, device=dev)
+            pos = torch.empty(k, dtype=torch.float32, device=dev)
+            ws_bytes = lib.mmcl_sim_lse_workspace_bytes(h, k, n_total, d)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib.mmcl_sim_lse_fwd(h, ptr(fa), k, ptr(stt.fb_all), n_total, d, sp, ptr(lse_a),
+                                       ptr(es_a), ptr(ws), ws_bytes, st), "mmcl_sim_lse_fwd")
+            check(lib.mmcl_sim_lse_fwd(h, ptr(fb), k, ptr(stt.fa_all), n_total, d, sp, ptr(lse_b),
+                                       ptr(es_b), ptr(ws), ws_bytes, st), "mmcl_sim_lse_fwd")
+            check(lib.mmcl_positive_logits(h, ptr(fa), k, ptr(stt.fb_all), n_total, d, off, sp,
+                                           ptr(pos), st), "mmcl_positive_logits")
+            check(lib.mmcl_pair_loss(h, ptr(lse_a), ptr(lse_b), ptr(es_a), ptr(es_b), ptr(pos), k,
+                                     plan.weight, float(plan.loss_rows), sp,
+                                     out2.data_ptr() + 8 * p, st), "mmcl_pair_loss")
+            stt.lse_a, stt.lse_b, stt.pos = lse_a, lse_b, pos
+
+        # global loss: every rank reports the mean over all N rows (contrastive.py:334-337)
+        if world > 1 and not m.local_loss:
+            check(lib.mmcl_all_reduce_sum_f32(h, ptr(out2), out2.numel(), st),
+                  "mmcl_all_reduce_sum_f32")
+            losses_present = any(s_.plan.n_total > 0 for s_ in self.states)
+
+        # backward needs the log-sum-exp of every row of S (column terms).  Gathered here, in
+        # forward, so that backward issues no collective at all (a rank whose loss is a constant
+        # 0 never runs backward; the reference deadlocks in that situation).
+        if need_grad and world > 1:
+            for stt in self.states:
+                plan = stt.plan
+                if plan.col_denominators() is None:
+                    continue
+                for name in ("lse_a", "lse_b"):
+                    loc = getattr(stt, name, None) if plan.b_local > 0 else None
+                    full = torch.empty(plan.n_total, dtype=torch.float32, device=dev)
+                    if loc is not None:
+                        full[plan.offset:plan.offset + plan.b_local].copy_(loc)
+                    check(lib.mmcl_all_gather_rows(h, full.data_ptr() + 4 * plan.offset, ptr(full),
+                                                   counts_array(plan.counts), 4, st),
+                          "mmcl_all_gather_rows")
+                    setattr(stt, name + "_all", full)
+        self.losses_present = losses_present
+        loss = out2[:, 0].sum()
+        dscale = out2[:, 1].clone() if scale.numel() > 1 else out2[:, 1].sum()
+        return loss, dscale
+
+    # ------------------------------------------------------------------------------------
+    def _check_global_order(self, ma, mb, ids_of, counts, world):
+        """The reference matches the *gathered* ids again (contrastive.py:310-313).  The fused
+        path needs the result only to confirm that the global match list is the concatenation of
+        the local ones (true unless an example id occurs on two ranks)."""
+        lib = _lib.load()
+        key = ("gcheck", ma.name, mb.name)
+        cache = self.__dict__.setdefault("_gcheck", {})
+        if key in cache:
+            return
+        dev, h, st = self.dev, self.h, _stream(self.dev)
+
+        def gather_ids(name):
+            ck = ("ids", name)
+            if ck in cache:
+                return cache[ck]
+            loc = ids_of(name) if name in self.example_ids else torch.empty(0, 2, dtype=torch.long,
+                                                                            device=dev)
+            sizes = all_gather_ints(torch.tensor([loc.shape[0]], device=dev), world).view(-1).cpu()
+            sizes = [int(x) for x in sizes]
+            full = torch.empty(sum(sizes), 2, dtype=torch.long, device=dev)
+            off = sum(sizes[: dist.get_rank()])
+            if loc.shape[0]:
+                full[off:off + loc.shape[0]].copy_(loc)
+            check(lib.mmcl_all_gather_rows(h, full.data_ptr() + off * 16, ptr(full),
+                                           counts_array(sizes), 16, st), "mmcl_all_gather_rows")
+            cache[ck] = full
+            return full
+
+        ga, gb = gather_ids(ma.name), gather_ids(mb.name)
+        mt = _Match(h, ga, gb, capacity=1)
+        k_global = int(mt.info[0].item())
+        cache[key] = k_global
+        if k_global != sum(counts):
+            raise NotImplementedError(
+                f"pair ({ma.name}, {mb.name}): {k_global} matches across ranks but {sum(counts)} "
+                "within ranks -- some example id occurs on more than one rank. The reference's "
+                "labels are mis-aligned in that case (SURVEY.md Appendix B); the fused path "
+                "refuses it instead of silently computing something else.")
+
+    # ------------------------------------------------------------------------------------
+    def backward(self, gout: torch.Tensor):
+        lib = _lib.load()
+        dev, h = self.dev, self.h
+        st = _stream(dev)
+        m = self.m
+        gout = gout.detach().to(device=dev, dtype=torch.float32).contiguous()
+        grads32: dict = {}
+        for stt in self.states:
+            plan = stt.plan
+            k, n, off = plan.b_local, plan.n_total, plan.offset
+            if k == 0:
+                continue
+            d = stt.fa_all.shape[1]
+            sp = self.scale.data_ptr() + 4 * stt.scale_index
+            fa = stt.fa_all[off:off + k]
+            fb = stt.fb_all[off:off + k]
+            cden = plan.col_denominators()
+
+            def offsets(lse_loc, lse_all):
+                o_row = torch.empty(k, dtype=torch.float32, device=dev)
+                check(lib.mmcl_make_offsets(h, ptr(lse_loc), k, None, plan.row_denominator(),
+                                            ptr(o_row), st), "mmcl_make_offsets")
+                return o_row
+
+            def col_offsets(lse_loc, lse_all):
+                if cden is None:
+                    return None
+                src = lse_all if plan.world > 1 else lse_loc
+                o = torch.empty(n, dtype=torch.float32, device=dev)
+                if len(set(cden)) == 1:
+                    check(lib.mmcl_make_offsets(h, ptr(src), n, None, cden[0], ptr(o), st),
+                          "mmcl_make_offsets")
+                else:
+                    den = torch.repeat_interleave(
+                        torch.tensor(cden, dtype=torch.float32, device=dev),
+                        torch.tensor(list(plan.counts), device=dev))
+                    check(lib.mmcl_make_offsets(h, ptr(src), n, ptr(den), 1.0, ptr(o), st),
+                          "mmcl_make_offsets")
+                return o
+
+            row_a = offsets(stt.lse_a, None)
+            row_b = offsets(stt.lse_b, None)
+            col_for_a = col_offsets(stt.lse_b, getattr(stt, "lse_b_all", None))  # columns of S
+            col_for_b = col_offsets(stt.lse_a, getattr(stt, "lse_a_all", None))  # rows of S
+            pc = plan.positive_coefficient()
+            for (key, x, y_all, o_row, o_col, partner, inv, idx) in (
+                (stt.key_a, fa, stt.fb_all, row_a, col_for_a, fb, stt.inv_a, stt.idx_a),
+                (stt.key_b, fb, stt.fa_all, row_b, col_for_b, fa, stt.inv_b, stt.idx_b),
+            ):
+                src = self.embs[key]
+                if not src.requires_grad:
+                    continue
+                dacc = torch.zeros(k, d, dtype=torch.float32, device=dev)
+                check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(o_row),
+                                            ptr(o_col), ptr(dacc), st), "mmcl_sim_grad_bwd")
+                if key not in grads32:
+                    grads32[key] = torch.zeros(src.shape, dtype=torch.float32, device=dev)
+                s_c = src.detach().contiguous()
+                check(lib.mmcl_unpack_grad(h, ptr(dacc), ptr(partner), k, d, plan.weight, pc,
+                                           ptr(gout), sp, ptr(s_c), _DTYPES[s_c.dtype], ptr(inv),
+                                           int(m.l2_normalize), ptr(idx), ptr(grads32[key]), st),
+                      "mmcl_unpack_grad")
+        out = []
+        for key in self.keys:
+            src = self.embs[key]
+            if not src.requires_grad:
+                out.append(None)
+            elif key in grads32:
+                out.append(grads32[key].to(src.dtype))
+            else:
+                out.append(torch.zeros_like(src))
+        self.states = []
+        return out
+
+
+class ContrastiveLoss(nn.Module):
+    """Contrastive Loss (fused B200 implementation).
+
+    Parameters mirror mmlearn/modules/losses/contrastive.py:23-37.
+
+    Parameters
+    ----------
+    l2_normalize : bool, optional, default=False
+        Whether to L2 normalize the features.
+    local_loss : bool, optional, default=False
+        Whether to calculate the loss locally i.e. ``local_features@global_features``.
+    gather_with_grad : bool, optional, default=False
+        Whether to gather tensors with gradients.
+    modality_alignment : bool, optional, default=False
+        Whether to include the modality alignment loss (not part of the fused path; raises).
+    cache_labels : bool, optional, default=False
+        Whether to cache the labels.
+    """
+
+    def __init__(
+        self,
+        l2_normalize: bool = False,
+        local_loss: bool = False,
+        gather_with_grad: bool = False,
+        modality_alignment: bool = False,
+        cache_labels: bool = False,
+    ):
+        super().__init__()
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.l2_normalize = l2_normalize
+        self.modality_alignment = modality_alignment
+        # cache state (same attributes as contrastive.py:55-57; not part of state_dict)
+        self._prev_num_logits = 0
+        self._labels: dict = {}
+
+    def _remember_labels(self, plan: PairPlan, device) -> None:
+        """contrastive.py:190-219: rebuild when the logit width changes or the device is new."""
+        n = plan.n_total if plan.n_logits is None else plan.n_logits
+        if self._prev_num_logits != n or device not in self._labels:
+            self._labels[device] = plan.labels(device)
+            self._prev_num_logits = n
+
+    def get_ground_truth(self, plan: PairPlan, device) -> torch.Tensor:
+        """Labels of one pair on this rank (``_get_ground_truth``, contrastive.py:162-219)."""
+        return plan.labels(device)
+
+    def forward(
+        self,
+        embeddings: dict[str, torch.Tensor],
+        example_ids: dict[str, torch.Tensor],
+        logit_scale: torch.Tensor,
+        modality_loss_pairs: list[LossPairSpec],
+    ) -> torch.Tensor:
+        """Calculate the contrastive loss (same contract as contrastive.py:59-85)."""
+        if self.modality_alignment:
+            raise NotImplementedError(
+                "modality_alignment=True is outside the fused hot path (SURVEY.md section 8, row "
+                "a11); use the reference module for that term.")
+        if not embeddings:
+            raise ValueError("embeddings is empty")
+        keys = list(embeddings.keys())
+        embs = [embeddings[k] for k in keys]
+        for k, e in zip(keys, embs):
+            if not isinstance(e, torch.Tensor) or not e.is_cuda:
+                raise ValueError(
+                    f"embedding '{k}' is not a CUDA tensor: mmlearn_b200 runs sm_100a kernels only "
+                    "and has no CPU fallback")
+            if e.ndim != 2 or e.shape[-1] % 8 != 0 or e.shape[-1] > 2048:
+                raise ValueError(
+                    f"embedding '{k}' must be [batch, d] with d a multiple of 8 (<= 2048), got "
+                    f"{tuple(e.shape)}")
+            if e.dtype not in _DTYPES:
+                raise ValueError(f"embedding '{k}' has unsupported dtype {e.dtype}")
+        if len({e.shape[-1] for e in embs}) != 1:
+            raise ValueError("Expected all embeddings to have the same dimension.")
+        if not isinstance(logit_scale, torch.Tensor):
+            logit_scale = torch.tensor(float(logit_scale), device=embs[0].device)
+        run = _Run(self, keys, example_ids, list(modality_loss_pairs))
+        loss = _FusedContrastiveFn.apply(run, logit_scale, *embs)
+        if not run.losses_present:
+            # no loss to compute (e.g. no paired data in batch): contrastive.py:151-158
+            return torch.zeros((), device=logit_scale.device, dtype=embs[0].dtype)
+        return loss
+
+
+FusedContrastiveLoss = ContrastiveLoss
+
+try:  # pragma: no cover - hydra-zen / mmlearn are not installable in the build image
+    from mmlearn.conf import external_store  # type: ignore
+
+    external_store(ContrastiveLoss, name="FusedContrastiveLoss", group="modules/losses",
+                   provider="mmlearn_b200")
+except Exception:  # noqa: BLE001
+    pass

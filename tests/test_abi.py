@@ -1,0 +1,49 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports exactly the symbols
+include/mmcl.h declares (no compute call is made here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "mmcl.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmcl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    from mmlearn_b200 import _lib
+
+    assert _declared() == sorted(_lib.SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    from mmlearn_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    lib = _lib.load()
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert lib.mmcl_version() == 100
+    # argument validation happens before any CUDA call: safe without a GPU
+    assert lib.mmcl_match_workspace_bytes(10, 10) > 0
+    assert lib.mmcl_nccl_unique_id(None) == -1
+    assert b"null uid" in lib.mmcl_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    fn = ContrastiveLoss()
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        fn({"rgb_embedding": torch.randn(4, 8), "text_embedding": torch.randn(4, 8)},
+           {"rgb": torch.zeros(4, 2, dtype=torch.long), "text": torch.zeros(4, 2, dtype=torch.long)},
+           torch.tensor(1.0), [LossPairSpec(("rgb", "text"))])

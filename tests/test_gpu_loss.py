@@ -1,0 +1,109 @@
+"""GPU parity of the drop-in module against (a) the golden outputs of the unmodified reference
+(tests/golden, single-process cases) and (b) the pinned oracle on larger seeded inputs.
+
+Tolerances are the north-star's: bf16 operands with fp32 accumulation, loss rel-err <= 1e-3,
+gradient-norm rel-err <= 1e-2, d(scale) rel-err <= 1e-2; labels / matched indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.contrastive_oracle import LossPairSpec as OPair
+from oracle.contrastive_oracle import contrastive_oracle, synthetic_inputs
+from tests.golden_util import case_names, load_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run_fused(emb, ids, scale, pairs, flags, dtype=torch.float32, scale_vec=None):
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    fn = ContrastiveLoss(modality_alignment=False, **flags)
+    leaves = {f"{m}_embedding": torch.as_tensor(v).to(DEV).to(dtype).requires_grad_(True)
+              for m, v in emb.items()}
+    idt = {m: torch.as_tensor(v).to(DEV) for m, v in ids.items()}
+    s = torch.tensor(scale if scale_vec is None else scale_vec, device=DEV, dtype=torch.float32,
+                     requires_grad=True)
+    loss = fn(leaves, idt, s, [LossPairSpec((a, b), w) for a, b, w in pairs])
+    if loss.requires_grad:
+        loss.backward()
+    torch.cuda.synchronize()
+    return fn, loss, leaves, s
+
+
+def _compare(loss, leaves, s, ref_loss, ref_grads, ref_ds):
+    assert float(loss) == pytest.approx(ref_loss, rel=1e-3, abs=1e-6)
+    for k, v in leaves.items():
+        r = torch.as_tensor(ref_grads[k]).float()
+        g = v.grad.float().cpu() if v.grad is not None else torch.zeros_like(r)
+        if float(r.norm()) == 0:
+            assert float(g.norm()) == 0
+            continue
+        assert float(g.norm()) == pytest.approx(float(r.norm()), rel=1e-2)
+        assert float(torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0)) > 0.999
+    if s.grad is not None:
+        assert np.allclose(s.grad.cpu().numpy(), np.asarray(ref_ds), rtol=1e-2, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in case_names() if n.startswith("w1_")])
+def test_golden_single_process(name):
+    case = load_case(name)
+    fn, loss, leaves, s = _run_fused(case["emb"][0], case["ids"][0], case["scale"], case["pairs"],
+                                     {k: v for k, v in case["flags"].items()})
+    ref = case["out"][0]
+    _compare(loss, leaves, s, float(ref["loss"]),
+             {k: ref[f"grad_{k}"] for k in leaves}, float(ref["dscale"]))
+    if "labels" in ref:
+        lab = next(iter(fn._labels.values()))
+        assert lab.dtype == torch.long and np.array_equal(lab.cpu().numpy(), ref["labels"])
+
+
+@pytest.mark.parametrize("n,d,dtype", [(256, 512, torch.float32), (2048, 512, torch.bfloat16),
+                                       (1000, 768, torch.bfloat16), (4096, 1024, torch.float16)])
+def test_vs_oracle(n, d, dtype):
+    emb, ids = synthetic_inputs(n, d)
+    ref = contrastive_oracle(emb, ids, 1 / 0.07, [OPair(("rgb", "text"))], l2_normalize=True,
+                             local_loss=True, gather_with_grad=True, fast_match=True)
+    e = {k.replace("_embedding", ""): v for k, v in emb[0].items()}
+    fn, loss, leaves, s = _run_fused(e, ids[0], 1 / 0.07, [("rgb", "text", 1.0)],
+                                     dict(l2_normalize=True, local_loss=True, gather_with_grad=True,
+                                          cache_labels=True), dtype=dtype)
+    _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0])
+    assert torch.equal(next(iter(fn._labels.values())).cpu(), torch.arange(n))
+
+
+def test_three_modalities_per_pair_scale():
+    # BASELINE config 4 shape (reduced): 3 modalities, per-pair scale and weight
+    emb, ids = synthetic_inputs(1024, 768, modalities=("rgb", "dna", "text"))
+    from mmlearn_b200 import Modalities
+
+    if not Modalities.has_modality("dna"):
+        Modalities.register_modality("dna")
+    pairs = [("rgb", "dna", 1.0), ("rgb", "text", 0.5), ("dna", "text", 2.0)]
+    scales = [1 / 0.07, 10.0, 50.0]
+    ref = contrastive_oracle(emb, ids, scales, [OPair((a, b), w) for a, b, w in pairs],
+                             l2_normalize=True, fast_match=True)
+    e = {k.replace("_embedding", ""): v for k, v in emb[0].items()}
+    fn, loss, leaves, s = _run_fused(e, ids[0], None, pairs, dict(l2_normalize=True),
+                                     dtype=torch.bfloat16, scale_vec=scales)
+    _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0])
+
+
+def test_eval_no_grad_and_no_pairs():
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    emb, ids = synthetic_inputs(300, 64)
+    fn = ContrastiveLoss(l2_normalize=True)
+    e = {k: v.to(DEV) for k, v in emb[0].items()}
+    i = {k: torch.from_numpy(v).to(DEV) for k, v in ids[0].items()}
+    with torch.no_grad():
+        loss = fn(e, i, torch.tensor(10.0, device=DEV), [LossPairSpec(("rgb", "text"))])
+    ref = contrastive_oracle(emb, ids, 10.0, [OPair(("rgb", "text"))], l2_normalize=True,
+                             want_grads=False)
+    assert float(loss) == pytest.approx(ref.losses[0], rel=1e-3)
+    # disjoint ids -> no pair -> 0.0 (contrastive.py:151-158)
+    i2 = dict(i)
+    i2["text"] = i["text"] + 10_000
+    z = fn(e, i2, torch.tensor(10.0, device=DEV), [LossPairSpec(("rgb", "text"))])
+    assert float(z) == 0.0 and z.dtype == e["rgb_embedding"].dtype
+    assert len(fn.state_dict()) == 0
