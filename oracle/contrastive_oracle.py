@@ -89,6 +89,7 @@ class OracleResult:
     losses: list  # per rank: python float (fp64 of the torch scalar)
     grads: list  # per rank: dict emb_key -> torch.Tensor (same shape as the input)
     dscale: list  # per rank: float
+    dscale_gross: list  # per rank: sum_ij |dL/dS_ij| |S_ij| / s  (conditioning scale of dscale)
     labels: list  # per rank: list (per pair) of np.int64 arrays (or None if the pair is skipped)
     matched: list  # per rank: list (per pair) of (idx_a, idx_b) local index arrays
 
@@ -159,6 +160,7 @@ def contrastive_oracle(
     all_ids = gathered_ids() if W > 1 else ids_np[0]
 
     losses_t, labels_out, matched_out = [], [], []
+    gross = [0.0] * W
     for rank in range(W):
         all_emb = gathered_for(rank)
         emb = local[rank]
@@ -236,6 +238,13 @@ def contrastive_oracle(
                     (F.cross_entropy(logits_a, lt) + F.cross_entropy(logits_b, lt))
                     / 2 * pair.weight
                 )  # contrastive.py:134-144
+                with torch.no_grad():
+                    for lg in (logits_a, logits_b):
+                        g = torch.softmax(lg, dim=1)
+                        g[torch.arange(lt.numel()), lt] -= 1.0
+                        gross[rank] += float(
+                            (g.abs() * lg.abs()).sum() * abs(pair.weight) / (2 * lt.numel())
+                            / abs(float(s)))
         if not rank_losses:
             rank_losses.append(torch.zeros((), dtype=dtype))  # contrastive.py:151-158
         losses_t.append(torch.stack(rank_losses).sum())
@@ -259,6 +268,7 @@ def contrastive_oracle(
         losses=[float(l.detach().double()) for l in losses_t],
         grads=grads,
         dscale=dscale,
+        dscale_gross=gross,
         labels=labels_out,
         matched=matched_out,
     )

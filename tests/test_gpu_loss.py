@@ -31,7 +31,9 @@ def _run_fused(emb, ids, scale, pairs, flags, dtype=torch.float32, scale_vec=Non
     return fn, loss, leaves, s
 
 
-def _compare(loss, leaves, s, ref_loss, ref_grads, ref_ds):
+def _compare(loss, leaves, s, ref_loss, ref_grads, ref_ds, ds_gross=0.0):
+    """d(loss)/d(scale) = sum_ij G_ij S_ij / s is a signed sum that nearly cancels close to the
+    optimum of the scale, so its tolerance is 1e-2 relative plus 2e-3 of the un-signed sum."""
     assert float(loss) == pytest.approx(ref_loss, rel=1e-3, abs=1e-6)
     for k, v in leaves.items():
         r = torch.as_tensor(ref_grads[k]).float()
@@ -42,7 +44,8 @@ def _compare(loss, leaves, s, ref_loss, ref_grads, ref_ds):
         assert float(g.norm()) == pytest.approx(float(r.norm()), rel=1e-2)
         assert float(torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0)) > 0.999
     if s.grad is not None:
-        assert np.allclose(s.grad.cpu().numpy(), np.asarray(ref_ds), rtol=1e-2, atol=1e-6)
+        assert np.allclose(s.grad.cpu().numpy(), np.asarray(ref_ds), rtol=1e-2,
+                           atol=1e-6 + 2e-3 * ds_gross)
 
 
 @pytest.mark.parametrize("name", [n for n in case_names() if n.startswith("w1_")])
@@ -51,8 +54,12 @@ def test_golden_single_process(name):
     fn, loss, leaves, s = _run_fused(case["emb"][0], case["ids"][0], case["scale"], case["pairs"],
                                      {k: v for k, v in case["flags"].items()})
     ref = case["out"][0]
+    orc = contrastive_oracle(
+        [{f"{m}_embedding": torch.from_numpy(v) for m, v in case["emb"][0].items()}], case["ids"],
+        case["scale"], [OPair((a, b), w) for a, b, w in case["pairs"]],
+        l2_normalize=case["flags"]["l2_normalize"], want_grads=False)
     _compare(loss, leaves, s, float(ref["loss"]),
-             {k: ref[f"grad_{k}"] for k in leaves}, float(ref["dscale"]))
+             {k: ref[f"grad_{k}"] for k in leaves}, float(ref["dscale"]), orc.dscale_gross[0])
     if "labels" in ref:
         lab = next(iter(fn._labels.values()))
         assert lab.dtype == torch.long and np.array_equal(lab.cpu().numpy(), ref["labels"])
@@ -68,7 +75,7 @@ def test_vs_oracle(n, d, dtype):
     fn, loss, leaves, s = _run_fused(e, ids[0], 1 / 0.07, [("rgb", "text", 1.0)],
                                      dict(l2_normalize=True, local_loss=True, gather_with_grad=True,
                                           cache_labels=True), dtype=dtype)
-    _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0])
+    _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
     assert torch.equal(next(iter(fn._labels.values())).cpu(), torch.arange(n))
 
 
@@ -86,7 +93,7 @@ def test_three_modalities_per_pair_scale():
     e = {k.replace("_embedding", ""): v for k, v in emb[0].items()}
     fn, loss, leaves, s = _run_fused(e, ids[0], None, pairs, dict(l2_normalize=True),
                                      dtype=torch.bfloat16, scale_vec=scales)
-    _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0])
+    _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
 
 
 def test_eval_no_grad_and_no_pairs():
