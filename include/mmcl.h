@@ -39,6 +39,8 @@ typedef void* mmcl_stream; /* cudaStream_t */
 
 int mmcl_version(void);
 const char* mmcl_last_error(void);
+/* Diagnostic: number of CUDA kernels this library has launched in this process so far. */
+int64_t mmcl_kernel_launches(void);
 
 /* Size of the opaque NCCL unique id (ncclUniqueId) the caller broadcasts to all ranks. */
 #define MMCL_NCCL_UID_BYTES 128

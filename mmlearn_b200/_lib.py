@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libmmcl.so")
 SYMBOLS = {
     "mmcl_version": (c_int, []),
     "mmcl_last_error": (c_char_p, []),
+    "mmcl_kernel_launches": (c_int64, []),
     "mmcl_nccl_unique_id": (c_int, [c_void_p]),
     "mmcl_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p]),
     "mmcl_destroy": (c_int, [c_void_p]),

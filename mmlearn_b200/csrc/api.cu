@@ -8,6 +8,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <atomic>
 
 #include "../../include/mmcl.h"
 #include "kernels.h"
@@ -57,9 +58,17 @@ struct DeviceGuard {
 
 }  // namespace
 
+namespace mmcl {
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace mmcl
+
 extern "C" {
 
 int mmcl_version(void) { return MMCL_VERSION; }
+
+int64_t mmcl_kernel_launches(void) { return launches_so_far(); }
 
 const char* mmcl_last_error(void) { return g_err.c_str(); }
 

@@ -220,6 +220,7 @@ cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows,
     pack_rows_kernel<1><<<blocks, wpb * 32, 0, stream>>>(src, src_rows, int(d), idx, n_out, normalize, dst, inv_norm);
   else
     pack_rows_kernel<2><<<blocks, wpb * 32, 0, stream>>>(src, src_rows, int(d), idx, n_out, normalize, dst, inv_norm);
+  count_launches(1);
   return cudaGetLastError();
 }
 
@@ -231,6 +232,7 @@ cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, l
   positive_logits_kernel<<<unsigned((nq + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(q), nq, static_cast<const __nv_bfloat16*>(k), nk, int(d),
       label_offset, scale, pos);
+  count_launches(1);
   return cudaGetLastError();
 }
 
@@ -240,6 +242,7 @@ cudaError_t launch_pair_loss(const float* lse_a, const float* lse_b, const float
   if (n == 0) return cudaSuccess;
   pair_loss_kernel<<<1, 1024, 0, stream>>>(lse_a, lse_b, esum_a, esum_b, pos, n,
                                            weight / (2.0 * n_norm), scale, out2);
+  count_launches(1);
   return cudaGetLastError();
 }
 
@@ -248,6 +251,7 @@ cudaError_t launch_make_offsets(const float* lse, long long n, const float* deno
   if (n == 0) return cudaSuccess;
   make_offsets_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
       lse, n, denom_vec, denom_vec ? 0.f : (float)log2(denom_scalar), off);
+  count_launches(1);
   return cudaGetLastError();
 }
 
@@ -266,6 +270,7 @@ cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16, long
     unpack_grad_kernel<1><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
   else
     unpack_grad_kernel<2><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+  count_launches(1);
   return cudaGetLastError();
 }
 

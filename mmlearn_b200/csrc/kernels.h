@@ -6,6 +6,10 @@
 
 namespace mmcl {
 
+// process-wide count of kernel launches (diagnostic, see mmcl_kernel_launches)
+void count_launches(int n);
+long long launches_so_far();
+
 // sim_fwd.cu
 size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d);
 cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const void* k,

@@ -198,6 +198,7 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   auto* info = reinterpret_cast<long long*>(out_info);
   info_init_kernel<<<1, 1, 0, stream>>>(info, n, m);
+  count_launches(1);
   if (n == 0 || m == 0) return cudaGetLastError();
   MatchWs w;
   if (carve(&w, workspace, n, m) > workspace_bytes) return cudaErrorInvalidValue;
@@ -214,6 +215,7 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
   scan_kernel<<<1, 1024, 0, stream>>>(w.cnt_a, w.off_a, n, info);
   emit_kernel<<<blocks(n), B, 0, stream>>>(w, n, m, reinterpret_cast<long long*>(out_a),
                                            reinterpret_cast<long long*>(out_b), capacity, info);
+  count_launches(8);
   return cudaGetLastError();
 }
 

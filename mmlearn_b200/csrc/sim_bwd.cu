@@ -340,6 +340,7 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
     if (e != cudaSuccess) return e;
     sim_grad_bwd_kernel<false><<<int(ctas), 256, smem, stream>>>(tmX, tmY256, tmY64, p);
   }
+  count_launches(1);
   return cudaGetLastError();
 }
 

@@ -345,6 +345,7 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   lse_combine_kernel<<<(p.nq + 255) / 256, 256, 0, stream>>>(p, lse, esum);
+  count_launches(2);
   return cudaGetLastError();
 }
 
