@@ -245,6 +245,8 @@ def main():
             torch.randn(N, d, device=dev, generator=torch.Generator(device=dev).manual_seed(7)),
             dim=-1).to(torch.bfloat16)
         sc = torch.tensor([1 / 0.07], device=dev)
+        xinv = torch.ones(b, device=dev)
+        yinv = torch.ones(N, device=dev)
         off_r = torch.full((b,), 30.0, device=dev)
         off_c = torch.full((N,), 30.0, device=dev)
         dx = torch.zeros(b, d, device=dev)
@@ -256,8 +258,8 @@ def main():
             torch.cuda.synchronize()
             if i >= 2:
                 kev[i - 2][0].record()
-            check(lib.mmcl_sim_grad_bwd(hnd, ptr(x), b, ptr(y), N, d, ptr(sc), ptr(off_r),
-                                        ptr(off_c), ptr(dx), st), "bwd")
+            check(lib.mmcl_sim_grad_bwd(hnd, ptr(x), b, ptr(y), N, d, ptr(sc), ptr(xinv), ptr(yinv),
+                                        ptr(off_r), ptr(off_c), ptr(dx), st), "bwd")
             if i >= 2:
                 kev[i - 2][1].record()
         torch.cuda.synchronize()

@@ -73,8 +73,10 @@ int mmcl_match_ids(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_
                    mmcl_stream stream);
 
 /* ------------------------------------------------------------------------------------------
- * Row packing: dst[i,:] = bf16( normalise?( src[idx[i],:] ) ), inv_norm[i] = 1/max(|src row|,1e-12)
- * (1.0 when normalize == 0).  idx == NULL means idx[i] = i.
+ * Row packing: dst[i,:] = bf16( src[idx[i],:] ), inv_norm[i] = 1/max(|src row|,1e-12)
+ * (1.0 when normalize == 0).  idx == NULL means idx[i] = i.  The rows stay un-normalised: the
+ * fp32 factors inv_norm are applied inside the GEMM epilogues (mmcl_sim_lse_fwd /
+ * mmcl_sim_grad_bwd), so bf16 inputs reach the tensor cores without a second rounding.
  * Replaces: F.normalize at contrastive.py:89-90 and the row selection `emb[indices]` at
  * contrastive.py:290-291,318-319; writes straight into the caller's gather buffer.
  * ------------------------------------------------------------------------------------------ */
@@ -98,23 +100,26 @@ int mmcl_all_reduce_sum_f32(mmcl_handle* h, float* buf, int64_t n, mmcl_stream s
 
 /* ------------------------------------------------------------------------------------------
  * Fused similarity + online log-sum-exp (forward hot kernel, tcgen05/TMEM/TMA).
- * For q [nq,d], k [nk,d] (bf16 row-major, d % 8 == 0) and s = *scale (device fp32):
- *   lse[i]  = log sum_j exp(s * q_i . k_j)
- *   esum[i] = sum_j softmax_j(s * q_i . k_j) * (s * q_i . k_j)       (gives d loss / d s)
- * The nq x nk logit matrix only ever exists as 128x128 fp32 tiles in tensor memory.
+ * For q [nq,d], k [nk,d] (bf16 row-major, d % 8 == 0), s = *scale (device fp32) and optional
+ * per-row factors qinv [nq], kinv [nk] (NULL = 1; the L2-normalisation and the logit scale are
+ * folded into the epilogue), with S_ij = s * qinv_i * kinv_j * (q_i . k_j):
+ *   lse[i]  = log sum_j exp(S_ij)
+ *   esum[i] = sum_j softmax_j(S_ij) * S_ij                           (gives d loss / d s)
+ * The nq x nk logit matrix only ever exists as 128x256 fp32 tiles in tensor memory.
  * Replaces: _safe_matmul + logit_scale multiply (contrastive.py:327-340) and the
  * log-softmax half of F.cross_entropy (contrastive.py:138-139).
  * ------------------------------------------------------------------------------------------ */
 size_t mmcl_sim_lse_workspace_bytes(mmcl_handle* h, int64_t nq, int64_t nk, int64_t d);
 int mmcl_sim_lse_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
-                     int64_t nk, int64_t d, const float* scale, float* lse, float* esum,
-                     void* workspace, size_t workspace_bytes, mmcl_stream stream);
+                     int64_t nk, int64_t d, const float* scale, const float* qinv,
+                     const float* kinv, float* lse, float* esum, void* workspace,
+                     size_t workspace_bytes, mmcl_stream stream);
 
-/* pos[i] = s * q_i . k_{label_offset + i}  (the positive logit; labels are off_r + i,
+/* pos[i] = S_{i, label_offset + i}  (the positive logit; labels are off_r + i,
  * contrastive.py:194-212).  fp32 accumulation over the same bf16 rows the GEMM reads. */
 int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
                          int64_t nk, int64_t d, int64_t label_offset, const float* scale,
-                         float* pos, mmcl_stream stream);
+                         const float* qinv, const float* kinv, float* pos, mmcl_stream stream);
 
 /* Pair loss and d loss / d s from the row statistics of both directions
  * (contrastive.py:135-144):  out[0] += weight/(2 n) * sum_i (lse_a+lse_b-2 pos)[i]
@@ -125,9 +130,10 @@ int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const
                    const float* scale, float* out2, mmcl_stream stream);
 
 /* ------------------------------------------------------------------------------------------
- * Fused recompute backward (hot kernel, tcgen05/TMEM/TMA): for x [nx,d], y [ny,d] bf16 and
- * c = s*log2(e):
- *   dx[i,:] += sum_j ( 2^(c x_i.y_j - off_row[i]) + 2^(c x_i.y_j - off_col[j]) ) * y[j,:]
+ * Fused recompute backward (hot kernel, tcgen05/TMEM/TMA): for x [nx,d], y [ny,d] bf16,
+ * optional xinv [nx], yinv [ny] (NULL = 1) and L_ij = log2(e) * s * xinv_i * yinv_j * (x_i.y_j):
+ *   dx[i,:] += sum_j ( 2^(L_ij - off_row[i]) + 2^(L_ij - off_col[j]) ) * yinv_j * y[j,:]
+ * i.e. the gradient with respect to the NORMALISED row x_i/|x_i| (before the factor s).
  * Either offset vector may be NULL (term dropped).  With off_row = log2(e)*lse_row + log2(2 b)
  * the first term is softmax_row/(2b); with off_col likewise the column-normalised softmax.
  * dx is fp32 [nx,d] and must be zero-initialised (or hold a running sum) by the caller.
@@ -135,8 +141,9 @@ int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const
  * (contrastive.py:327-340,138-139); logit tiles are recomputed, never stored.
  * ------------------------------------------------------------------------------------------ */
 int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16,
-                      int64_t ny, int64_t d, const float* scale, const float* off_row,
-                      const float* off_col, float* dx, mmcl_stream stream);
+                      int64_t ny, int64_t d, const float* scale, const float* xinv,
+                      const float* yinv, const float* off_row, const float* off_col, float* dx,
+                      mmcl_stream stream);
 
 /* off[i] = log2(e) * lse[i] + log2(denom[i] or denom_scalar)  (helper for the call above) */
 int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* denom_vec,
@@ -144,13 +151,15 @@ int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* 
 
 /* ------------------------------------------------------------------------------------------
  * Gradient unpack for one modality side of one pair:
- *   g_hat[i,:] = coef * ( dacc[i,:] - pos_coef * partner[i,:] )        coef = weight*(*gout)*(*s)
+ *   g_hat[i,:] = coef * ( dacc[i,:] - pos_coef * partner_inv[i] * partner[i,:] )
+ *                                                                       coef = weight*(*gout)*(*s)
  *   g[i,:]     = normalise-backward(g_hat[i,:]; src row, inv_norm[i])  (if normalize)
  *   grad[idx[i],:] += g[i,:]                                           (fp32 atomics)
  * Replaces: backward of index-select (index_put accumulate), of F.normalize and the
  * positive-label term of cross_entropy's backward.
  * ------------------------------------------------------------------------------------------ */
-int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16, int64_t n,
+int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16,
+                     const float* partner_inv, int64_t n,
                      int64_t d, double weight, double pos_coef, const float* gout,
                      const float* scale, const void* src, int src_dtype, const float* inv_norm,
                      int normalize, const int64_t* idx, float* grad_f32, mmcl_stream stream);

@@ -32,16 +32,18 @@ SYMBOLS = {
     "mmcl_all_reduce_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "mmcl_sim_lse_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64, c_int64]),
     "mmcl_sim_lse_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
     "mmcl_positive_logits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
-                                     c_int64, c_void_p, c_void_p, c_void_p]),
+                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmcl_pair_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "mmcl_sim_grad_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "mmcl_make_offsets": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_double, c_void_p,
                                   c_void_p]),
-    "mmcl_unpack_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
+    "mmcl_unpack_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
                                  c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p]),
 }

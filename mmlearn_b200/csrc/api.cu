@@ -267,8 +267,9 @@ static int check_sim_args(const char* fn, const void* a, int64_t na, const void*
 }
 
 int mmcl_sim_lse_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
-                     int64_t nk, int64_t d, const float* scale, float* lse, float* esum,
-                     void* workspace, size_t workspace_bytes, mmcl_stream stream) {
+                     int64_t nk, int64_t d, const float* scale, const float* qinv,
+                     const float* kinv, float* lse, float* esum, void* workspace,
+                     size_t workspace_bytes, mmcl_stream stream) {
   REQUIRE(h && scale, "mmcl_sim_lse_fwd: null handle/scale");
   int rc = check_sim_args("mmcl_sim_lse_fwd", q_bf16, nq, k_bf16, nk, d);
   if (rc) return rc;
@@ -280,24 +281,24 @@ int mmcl_sim_lse_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void*
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   const char* err = nullptr;
-  cudaError_t e = launch_sim_lse_fwd(h->num_sms, q_bf16, nq, k_bf16, nk, d, scale, lse, esum,
-                                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream),
-                                     &err);
+  cudaError_t e = launch_sim_lse_fwd(h->num_sms, q_bf16, nq, k_bf16, nk, d, scale, qinv, kinv, lse,
+                                     esum, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream), &err);
   if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_lse_fwd");
   return MMCL_OK;
 }
 
 int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
                          int64_t nk, int64_t d, int64_t label_offset, const float* scale,
-                         float* pos, mmcl_stream stream) {
+                         const float* qinv, const float* kinv, float* pos, mmcl_stream stream) {
   REQUIRE(h && scale, "mmcl_positive_logits: null handle/scale");
   int rc = check_sim_args("mmcl_positive_logits", q_bf16, nq, k_bf16, nk, d);
   if (rc) return rc;
   REQUIRE(nq == 0 || pos, "mmcl_positive_logits: null pos");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  cudaError_t e = launch_positive_logits(q_bf16, nq, k_bf16, nk, d, label_offset, scale, pos,
-                                         static_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_positive_logits(q_bf16, nq, k_bf16, nk, d, label_offset, scale, qinv,
+                                         kinv, pos, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_positive_logits");
 }
 
@@ -315,8 +316,9 @@ int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const
 }
 
 int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16,
-                      int64_t ny, int64_t d, const float* scale, const float* off_row,
-                      const float* off_col, float* dx, mmcl_stream stream) {
+                      int64_t ny, int64_t d, const float* scale, const float* xinv,
+                      const float* yinv, const float* off_row, const float* off_col, float* dx,
+                      mmcl_stream stream) {
   REQUIRE(h && scale, "mmcl_sim_grad_bwd: null handle/scale");
   int rc = check_sim_args("mmcl_sim_grad_bwd", x_bf16, nx, y_bf16, ny, d);
   if (rc) return rc;
@@ -325,8 +327,9 @@ int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   const char* err = nullptr;
-  cudaError_t e = launch_sim_grad_bwd(h->num_sms, x_bf16, nx, y_bf16, ny, d, scale, off_row,
-                                      off_col, dx, static_cast<cudaStream_t>(stream), &err);
+  cudaError_t e = launch_sim_grad_bwd(h->num_sms, x_bf16, nx, y_bf16, ny, d, scale, xinv, yinv,
+                                      off_row, off_col, dx, static_cast<cudaStream_t>(stream),
+                                      &err);
   if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_grad_bwd");
   return MMCL_OK;
 }
@@ -343,7 +346,8 @@ int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* 
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_make_offsets");
 }
 
-int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16, int64_t n,
+int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16,
+                     const float* partner_inv, int64_t n,
                      int64_t d, double weight, double pos_coef, const float* gout,
                      const float* scale, const void* src, int src_dtype, const float* inv_norm,
                      int normalize, const int64_t* idx, float* grad_f32, mmcl_stream stream) {
@@ -354,7 +358,8 @@ int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16
   REQUIRE(!normalize || (src && inv_norm), "mmcl_unpack_grad: normalize needs src and inv_norm");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  cudaError_t e = launch_unpack_grad(dacc, partner_bf16, n, d, weight, pos_coef, gout, scale, src,
+  cudaError_t e = launch_unpack_grad(dacc, partner_bf16, partner_inv, n, d, weight, pos_coef, gout,
+                                     scale, src,
                                      src_dtype, inv_norm, normalize, idx, grad_f32,
                                      static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_unpack_grad");

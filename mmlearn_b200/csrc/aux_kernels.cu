@@ -78,10 +78,11 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, long long src_row
     float f[8];
     load8<DT>(src, srow * d + c, f);
     uint4 o;
-    o.x = bf16x2(f[0] * inv, f[1] * inv);
-    o.y = bf16x2(f[2] * inv, f[3] * inv);
-    o.z = bf16x2(f[4] * inv, f[5] * inv);
-    o.w = bf16x2(f[6] * inv, f[7] * inv);
+    // raw values: the 1/||x|| factor is applied in fp32 inside the GEMM epilogues
+    o.x = bf16x2(f[0], f[1]);
+    o.y = bf16x2(f[2], f[3]);
+    o.z = bf16x2(f[4], f[5]);
+    o.w = bf16x2(f[6], f[7]);
     *reinterpret_cast<uint4*>(dst + row * d + c) = o;
   }
   if (inv_norm && lane == 0) inv_norm[row] = inv;
@@ -90,7 +91,8 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, long long src_row
 __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long long nq,
                                        const __nv_bfloat16* __restrict__ k, long long nk, int d,
                                        long long label_offset, const float* __restrict__ scale,
-                                       float* __restrict__ pos) {
+                                       const float* __restrict__ qinv,
+                                       const float* __restrict__ kinv, float* __restrict__ pos) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nq) return;
@@ -106,7 +108,12 @@ __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) pos[row] = acc * (*scale);
+  if (lane == 0) {
+    float f = *scale;
+    if (qinv) f *= qinv[row];
+    if (kinv && krow >= 0 && krow < nk) f *= kinv[krow];
+    pos[row] = acc * f;
+  }
 }
 
 __global__ void pair_loss_kernel(const float* __restrict__ lse_a, const float* __restrict__ lse_b,
@@ -154,7 +161,8 @@ __global__ void make_offsets_kernel(const float* __restrict__ lse, long long n,
 
 template <int DT>
 __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
-                                   const __nv_bfloat16* __restrict__ partner, long long n, int d,
+                                   const __nv_bfloat16* __restrict__ partner,
+                                   const float* __restrict__ partner_inv, long long n, int d,
                                    float weight, float pos_coef, const float* __restrict__ gout,
                                    const float* __restrict__ scale, const void* __restrict__ src,
                                    const float* __restrict__ inv_norm, int normalize,
@@ -168,6 +176,7 @@ __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
   float g[MAXV][8];
   float dot = 0.f;
   const float inv = normalize ? inv_norm[row] : 1.f;
+  const float pc = pos_coef * (partner_inv ? partner_inv[row] : 1.f);
   int nv = 0;
   for (int c = lane * 8; c < d; c += 256, ++nv) {
     float pa[8];
@@ -176,7 +185,7 @@ __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
     load8<1>(partner, row * d + c, pa);
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pos_coef * pa[i]);
+    for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pc * pa[i]);
     if (normalize) {
       float x[8];
       load8<DT>(src, srow * d + c, x);
@@ -226,12 +235,13 @@ cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows,
 
 cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, long long nk,
                                    long long d, long long label_offset, const float* scale,
-                                   float* pos, cudaStream_t stream) {
+                                   const float* qinv, const float* kinv, float* pos,
+                                   cudaStream_t stream) {
   if (nq == 0) return cudaSuccess;
   const int wpb = 8;
   positive_logits_kernel<<<unsigned((nq + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(q), nq, static_cast<const __nv_bfloat16*>(k), nk, int(d),
-      label_offset, scale, pos);
+      label_offset, scale, qinv, kinv, pos);
   count_launches(1);
   return cudaGetLastError();
 }
@@ -255,7 +265,8 @@ cudaError_t launch_make_offsets(const float* lse, long long n, const float* deno
   return cudaGetLastError();
 }
 
-cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16, long long n,
+cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16,
+                               const float* partner_inv, long long n,
                                long long d, double weight, double pos_coef, const float* gout,
                                const float* scale, const void* src, int src_dtype,
                                const float* inv_norm, int normalize, const int64_t* idx,
@@ -265,11 +276,11 @@ cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16, long
   const unsigned blocks = unsigned((n + wpb - 1) / wpb);
   auto* pb = static_cast<const __nv_bfloat16*>(partner_bf16);
   if (src_dtype == 0)
-    unpack_grad_kernel<0><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+    unpack_grad_kernel<0><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
   else if (src_dtype == 1)
-    unpack_grad_kernel<1><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+    unpack_grad_kernel<1><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
   else
-    unpack_grad_kernel<2><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+    unpack_grad_kernel<2><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
   count_launches(1);
   return cudaGetLastError();
 }

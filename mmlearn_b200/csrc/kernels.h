@@ -13,15 +13,15 @@ long long launches_so_far();
 // sim_fwd.cu
 size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d);
 cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const void* k,
-                               long long nk, long long d, const float* scale, float* lse,
-                               float* esum, void* workspace, size_t workspace_bytes,
-                               cudaStream_t stream, const char** err);
+                               long long nk, long long d, const float* scale, const float* qinv,
+                               const float* kinv, float* lse, float* esum, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream, const char** err);
 
 // sim_bwd.cu
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
-                                long long ny, long long d, const float* scale,
-                                const float* off_row, const float* off_col, float* dx,
-                                cudaStream_t stream, const char** err);
+                                long long ny, long long d, const float* scale, const float* xinv,
+                                const float* yinv, const float* off_row, const float* off_col,
+                                float* dx, cudaStream_t stream, const char** err);
 
 // aux_kernels.cu
 cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows, long long d,
@@ -29,13 +29,15 @@ cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows,
                              float* inv_norm, cudaStream_t stream);
 cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, long long nk,
                                    long long d, long long label_offset, const float* scale,
-                                   float* pos, cudaStream_t stream);
+                                   const float* qinv, const float* kinv, float* pos,
+                                   cudaStream_t stream);
 cudaError_t launch_pair_loss(const float* lse_a, const float* lse_b, const float* esum_a,
                              const float* esum_b, const float* pos, long long n, double weight,
                              double n_norm, const float* scale, float* out2, cudaStream_t stream);
 cudaError_t launch_make_offsets(const float* lse, long long n, const float* denom_vec,
                                 double denom_scalar, float* off, cudaStream_t stream);
-cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16, long long n,
+cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16,
+                               const float* partner_inv, long long n,
                                long long d, double weight, double pos_coef, const float* gout,
                                const float* scale, const void* src, int src_dtype,
                                const float* inv_norm, int normalize, const int64_t* idx,

@@ -36,27 +36,33 @@ struct BwdParams {
   int per_cta;
   int nstages;
   const float* scale;
+  const float* xinv;  // [nx] 1/||x_i|| or null
+  const float* yinv;  // [ny] 1/||y_j|| or null
   const float* off_row;
   const float* off_col;
   float* dx;
 };
 
+// cy[e] = (off_col[j], 1/||y_j||) for the 32 columns of the chunk.  The logit is
+// s * (x_i.y_j) * xinv_i * yinv_j; c = s*log2e*xinv_i.  G is multiplied by yinv_j so that the
+// second MMA can use the raw (un-normalised) Y tile.
 template <int MODE>  // 1: row term, 2: column term, 3: both
 __device__ __forceinline__ void g_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float c,
-                                        float offr, const float* offc) {
+                                        float offr, const float2* cy) {
 #pragma unroll
   for (int e = 0; e < 32; e += 2) {
-    const float x0 = __uint_as_float(v[e]), x1 = __uint_as_float(v[e + 1]);
+    const float4 f = *reinterpret_cast<const float4*>(cy + e);  // (offc0, yinv0, offc1, yinv1)
+    const float x0 = __uint_as_float(v[e]) * f.y, x1 = __uint_as_float(v[e + 1]) * f.w;
     float g0 = 0.f, g1 = 0.f;
     if (MODE & 1) {
       g0 = ex2f(fmaf(x0, c, -offr));
       g1 = ex2f(fmaf(x1, c, -offr));
     }
     if (MODE & 2) {
-      g0 += ex2f(fmaf(x0, c, -offc[e]));
-      g1 += ex2f(fmaf(x1, c, -offc[e + 1]));
+      g0 += ex2f(fmaf(x0, c, -f.x));
+      g1 += ex2f(fmaf(x1, c, -f.z));
     }
-    g[e >> 1] = pack_bf16x2(g0, g1);
+    g[e >> 1] = pack_bf16x2(g0 * f.y, g1 * f.w);
   }
 }
 
@@ -69,8 +75,8 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int stage_bytes = kXRes ? YBOX_BYTES : XCHUNK_BYTES + YBOX_BYTES;
   uint8_t* sX = smem;
   uint8_t* sStage = smem + (kXRes ? p.kchunks * XCHUNK_BYTES : 0);
-  float* sOffc = reinterpret_cast<float*>(sStage + p.nstages * stage_bytes);  // [2][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOffc + 2 * BNY);
+  float2* sCol = reinterpret_cast<float2*>(sStage + p.nstages * stage_bytes);  // [256] (offc, yinv)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + BNY);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
   uint64_t* x_full = bars + 2 * p.nstages;
@@ -220,7 +226,7 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int q = warp - 4;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;  // 0..127
-    const float c = (*p.scale) * LOG2E;
+    const float c0 = (*p.scale) * LOG2E;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
     uint32_t step = 0, seg = 0;
@@ -232,15 +238,17 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int xt = int(item / p.ndc), dc = int(item % p.ndc);
       const int grow = xt * BM + row;
       const float offr = (p.off_row && grow < p.nx) ? p.off_row[grow] : INFINITY;
+      const float c = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
       for (int yt = yt0; yt < yt1; ++yt) {
-        float* offc = sOffc + (step & 1) * BNY;
-        if (mode & 2) {
-          for (int j = et; j < BNY; j += 128) {
-            const int gy = yt * BNY + j;
-            offc[j] = gy < p.ny ? p.off_col[gy] : INFINITY;
-          }
+        named_bar_sync(1, 128);  // everyone is done reading the previous step's column data
+        for (int j = et; j < BNY; j += 128) {
+          const int gy = yt * BNY + j;
+          float2 v2;
+          v2.x = (p.off_col && gy < p.ny) ? p.off_col[gy] : INFINITY;
+          v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
+          sCol[j] = v2;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(2, 128);
         mbar_wait(s_full, step & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -249,11 +257,11 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tmem_ld_x32(tm_s + lane_base + ch * 32, v);
           tmem_ld_wait();
           if (mode == 3)
-            g_chunk<3>(v, g, c, offr, offc + ch * 32);
+            g_chunk<3>(v, g, c, offr, sCol + ch * 32);
           else if (mode == 1)
-            g_chunk<1>(v, g, c, offr, offc);
+            g_chunk<1>(v, g, c, offr, sCol + ch * 32);
           else
-            g_chunk<2>(v, g, c, offr, offc + ch * 32);
+            g_chunk<2>(v, g, c, offr, sCol + ch * 32);
           tmem_st_x16(tm_s + lane_base + ch * 16, g);
         }
         tmem_st_wait();
@@ -293,9 +301,9 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }  // namespace
 
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
-                                long long ny, long long d, const float* scale,
-                                const float* off_row, const float* off_col, float* dx,
-                                cudaStream_t stream, const char** err) {
+                                long long ny, long long d, const float* scale, const float* xinv,
+                                const float* yinv, const float* off_row, const float* off_col,
+                                float* dx, cudaStream_t stream, const char** err) {
   if (!off_row && !off_col) return cudaSuccess;  // G == 0
   BwdParams p;
   p.nx = int(nx);
@@ -310,6 +318,8 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
   p.per_cta = int((p.total + ctas - 1) / ctas);
   ctas = (p.total + p.per_cta - 1) / p.per_cta;
   p.scale = scale;
+  p.xinv = xinv;
+  p.yinv = yinv;
   p.off_row = off_row;
   p.off_col = off_col;
   p.dx = dx;

@@ -36,6 +36,8 @@ struct FwdParams {
   int max_slots;
   long long part_stride;  // floats between slots (= nqt * BM)
   const float* scale;
+  const float* qinv;  // [nq] 1/||q_i|| or null (rows already unit-norm / no normalisation)
+  const float* kinv;  // [nk] likewise for the keys
   float* part_m;
   float* part_l;
   float* part_t;
@@ -50,7 +52,8 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int stage_bytes = kQRes ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
   uint8_t* sQ = smem;
   uint8_t* sStage = smem + (kQRes ? p.kchunks * QCHUNK_BYTES : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.nstages * stage_bytes);
+  float* sKinv = reinterpret_cast<float*>(sStage + p.nstages * stage_bytes);  // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKinv + 2 * BN);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
   uint64_t* q_full = bars + 2 * p.nstages;
@@ -163,17 +166,26 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ================================ epilogue ====================================
     const int q = warp - 4;  // == warp % 4: TMEM lane quadrant
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;
     const float s = *p.scale;
-    const float c = s * LOG2E;
-    const bool neg = c < 0.f;
+    const bool neg = s < 0.f;
     uint32_t acc = 0;
     for (long long t = t_begin; t < t_end;) {
       const int qt = int(t / p.nkt), kt0 = int(t % p.nkt);
       int kt1 = kt0 + int(t_end - t);
       if (kt1 > p.nkt) kt1 = p.nkt;
       float m = -INFINITY, l = 0.f, tt = 0.f;
+      // logit = s * (q_i.k_j) * qinv_i * kinv_j ; c folds everything that depends on the row
+      const int grow = qt * BM + row;
+      const float c = s * LOG2E * ((p.qinv && grow < p.nq) ? p.qinv[grow] : 1.f);
       for (int kt = kt0; kt < kt1; ++kt) {
         const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
+        float* kv = sKinv + ab * BN;
+        for (int j = et; j < BN; j += 128) {
+          const int gk = kt * BN + j;
+          kv[j] = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+        }
+        named_bar_sync(1, 128);
         mbar_wait(&acc_full[ab], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
@@ -188,6 +200,17 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_arrive(&acc_empty[ab]);
           }
           const int cv = valid - ch * 32;
+          {
+            const float4* k4 = reinterpret_cast<const float4*>(kv + ch * 32);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 f = k4[e4];
+              v[4 * e4 + 0] = __float_as_uint(__uint_as_float(v[4 * e4 + 0]) * f.x);
+              v[4 * e4 + 1] = __float_as_uint(__uint_as_float(v[4 * e4 + 1]) * f.y);
+              v[4 * e4 + 2] = __float_as_uint(__uint_as_float(v[4 * e4 + 2]) * f.z);
+              v[4 * e4 + 3] = __float_as_uint(__uint_as_float(v[4 * e4 + 3]) * f.w);
+            }
+          }
           if (cv >= 32) {
             float ext = __uint_as_float(v[0]);
             if (!neg) {
@@ -269,7 +292,7 @@ __global__ void lse_combine_kernel(FwdParams p, float* __restrict__ lse, float* 
     L += p.part_l[o] * w;
     T += p.part_t[o] * w;
   }
-  const float sc = *p.scale;
+  const float sc = (*p.scale) * (p.qinv ? p.qinv[row] : 1.f);
   lse[row] = (M + log2f(L)) * LN2;
   if (esum) esum[row] = sc * T / L;
 }
@@ -286,14 +309,14 @@ int fwd_plan(int num_sms, long long nq, long long nk, long long d, FwdParams* p,
   p->tiles_per_cta = int((p->total_tiles + ctas - 1) / ctas);
   p->max_slots = (p->nkt + p->tiles_per_cta - 1) / p->tiles_per_cta + 1;
   p->part_stride = (long long)p->nqt * BM;
-  const size_t budget = 227 * 1024 - 256 /*barriers*/;
+  const size_t budget = 227 * 1024 - 256 /*barriers*/ - 2 * BN * sizeof(float) /*kinv*/;
   *qres = size_t(p->kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= budget;
   const size_t stage_bytes = *qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
   const size_t fixed = *qres ? size_t(p->kchunks) * QCHUNK_BYTES : 0;
   int ns = int((budget - fixed) / stage_bytes);
   if (ns > 8) ns = 8;
   p->nstages = ns;
-  *smem_bytes = fixed + ns * stage_bytes + 256;
+  *smem_bytes = fixed + ns * stage_bytes + 2 * BN * sizeof(float) + 256;
   return 0;
 }
 
@@ -308,9 +331,9 @@ size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long lon
 }
 
 cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const void* k,
-                               long long nk, long long d, const float* scale, float* lse,
-                               float* esum, void* workspace, size_t workspace_bytes,
-                               cudaStream_t stream, const char** err) {
+                               long long nk, long long d, const float* scale, const float* qinv,
+                               const float* kinv, float* lse, float* esum, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream, const char** err) {
   FwdParams p;
   bool qres;
   size_t smem;
@@ -321,6 +344,8 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
     return cudaErrorInvalidValue;
   }
   p.scale = scale;
+  p.qinv = qinv;
+  p.kinv = kinv;
   p.part_m = static_cast<float*>(workspace);
   p.part_l = p.part_m + size_t(p.max_slots) * p.part_stride;
   p.part_t = p.part_l + size_t(p.max_slots) * p.part_stride;

@@ -209,8 +209,7 @@ class _Run:
 
         # ---- 2. per pair: pack matched rows straight into the gather buffer, all-gather ----
         out2 = torch.zeros(P, 2, dtype=torch.float32, device=dev)
-        need_grad = torch.is_grad_enabled() and (
-            any(e.requires_grad for e in embs) or logit_scale.requires_grad)
+        need_grad = self.need_grad  # decided by the caller: grad mode is off inside Function.forward
         shared: dict = {}
         losses_present = False
         for p, pair in enumerate(self.pairs):
@@ -236,27 +235,36 @@ class _Run:
                 self._check_global_order(ma, mb, ids_of, counts, world)
 
             def gathered(key, idx, name):
+                """Raw bf16 rows of every rank's matched samples, [N, d], plus their fp32
+                inverse norms [N] (None without l2_normalize).  The local rows are packed
+                straight into their slot of the gather buffer; the all-gather is in place."""
                 ck = (key, "identity") if all_ident else None
                 if ck is not None and ck in shared:
                     return shared[ck]
                 src = self.embs[key] if key in self.embs else None
                 f_all = torch.empty(n_total, d, dtype=torch.bfloat16, device=dev)
-                inv = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
+                inv_all = (torch.empty(n_total, dtype=torch.float32, device=dev)
+                           if m.l2_normalize else None)
                 if k > 0:
                     s_c = src.detach().contiguous()
                     if s_c.dtype not in _DTYPES:
                         raise ValueError(f"unsupported embedding dtype {s_c.dtype}")
-                    check(lib.mmcl_pack_rows(h, ptr(s_c), _DTYPES[s_c.dtype], s_c.shape[0], d,
-                                             ptr(idx), k, int(m.l2_normalize),
-                                             f_all.data_ptr() + plan.offset * d * 2, ptr(inv), st),
-                          "mmcl_pack_rows")
+                    check(lib.mmcl_pack_rows(
+                        h, ptr(s_c), _DTYPES[s_c.dtype], s_c.shape[0], d, ptr(idx), k,
+                        int(m.l2_normalize), f_all.data_ptr() + plan.offset * d * 2,
+                        inv_all.data_ptr() + 4 * plan.offset if inv_all is not None else None, st),
+                        "mmcl_pack_rows")
                 if world > 1:
                     check(lib.mmcl_all_gather_rows(h, f_all.data_ptr() + plan.offset * d * 2,
                                                    ptr(f_all), counts_array(counts), d * 2, st),
                           "mmcl_all_gather_rows")
+                    if inv_all is not None:
+                        check(lib.mmcl_all_gather_rows(h, inv_all.data_ptr() + 4 * plan.offset,
+                                                       ptr(inv_all), counts_array(counts), 4, st),
+                              "mmcl_all_gather_rows")
                 if ck is not None:
-                    shared[ck] = (f_all, inv)
-                return f_all, inv
+                    shared[ck] = (f_all, inv_all)
+                return f_all, inv_all
 
             stt.fa_all, stt.inv_a = gathered(ma.embedding, stt.idx_a, ma.name)
             stt.fb_all, stt.inv_b = gathered(mb.embedding, stt.idx_b, mb.name)
@@ -279,12 +287,17 @@ class _Run:
             pos = torch.empty(k, dtype=torch.float32, device=dev)
             ws_bytes = lib.mmcl_sim_lse_workspace_bytes(h, k, n_total, d)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            check(lib.mmcl_sim_lse_fwd(h, ptr(fa), k, ptr(stt.fb_all), n_total, d, sp, ptr(lse_a),
-                                       ptr(es_a), ptr(ws), ws_bytes, st), "mmcl_sim_lse_fwd")
-            check(lib.mmcl_sim_lse_fwd(h, ptr(fb), k, ptr(stt.fa_all), n_total, d, sp, ptr(lse_b),
-                                       ptr(es_b), ptr(ws), ws_bytes, st), "mmcl_sim_lse_fwd")
+            ia_loc = stt.inv_a[off:off + k] if stt.inv_a is not None else None
+            ib_loc = stt.inv_b[off:off + k] if stt.inv_b is not None else None
+            check(lib.mmcl_sim_lse_fwd(h, ptr(fa), k, ptr(stt.fb_all), n_total, d, sp, ptr(ia_loc),
+                                       ptr(stt.inv_b), ptr(lse_a), ptr(es_a), ptr(ws), ws_bytes, st),
+                  "mmcl_sim_lse_fwd")
+            check(lib.mmcl_sim_lse_fwd(h, ptr(fb), k, ptr(stt.fa_all), n_total, d, sp, ptr(ib_loc),
+                                       ptr(stt.inv_a), ptr(lse_b), ptr(es_b), ptr(ws), ws_bytes, st),
+                  "mmcl_sim_lse_fwd")
             check(lib.mmcl_positive_logits(h, ptr(fa), k, ptr(stt.fb_all), n_total, d, off, sp,
-                                           ptr(pos), st), "mmcl_positive_logits")
+                                           ptr(ia_loc), ptr(stt.inv_b), ptr(pos), st),
+                  "mmcl_positive_logits")
             check(lib.mmcl_pair_loss(h, ptr(lse_a), ptr(lse_b), ptr(es_a), ptr(es_b), ptr(pos), k,
                                      plan.weight, float(plan.loss_rows), sp,
                                      out2.data_ptr() + 8 * p, st), "mmcl_pair_loss")
@@ -404,21 +417,26 @@ class _Run:
             col_for_a = col_offsets(stt.lse_b, getattr(stt, "lse_b_all", None))  # columns of S
             col_for_b = col_offsets(stt.lse_a, getattr(stt, "lse_a_all", None))  # rows of S
             pc = plan.positive_coefficient()
-            for (key, x, y_all, o_row, o_col, partner, inv, idx) in (
-                (stt.key_a, fa, stt.fb_all, row_a, col_for_a, fb, stt.inv_a, stt.idx_a),
-                (stt.key_b, fb, stt.fa_all, row_b, col_for_b, fa, stt.inv_b, stt.idx_b),
+            ia_loc = stt.inv_a[off:off + k] if stt.inv_a is not None else None
+            ib_loc = stt.inv_b[off:off + k] if stt.inv_b is not None else None
+            for (key, x, y_all, o_row, o_col, partner, inv, yinv, pinv, idx) in (
+                (stt.key_a, fa, stt.fb_all, row_a, col_for_a, fb, ia_loc, stt.inv_b, ib_loc,
+                 stt.idx_a),
+                (stt.key_b, fb, stt.fa_all, row_b, col_for_b, fa, ib_loc, stt.inv_a, ia_loc,
+                 stt.idx_b),
             ):
                 src = self.embs[key]
                 if not src.requires_grad:
                     continue
                 dacc = torch.zeros(k, d, dtype=torch.float32, device=dev)
-                check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(o_row),
-                                            ptr(o_col), ptr(dacc), st), "mmcl_sim_grad_bwd")
+                check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(inv), ptr(yinv),
+                                            ptr(o_row), ptr(o_col), ptr(dacc), st),
+                      "mmcl_sim_grad_bwd")
                 if key not in grads32:
                     grads32[key] = torch.zeros(src.shape, dtype=torch.float32, device=dev)
                 s_c = src.detach().contiguous()
-                check(lib.mmcl_unpack_grad(h, ptr(dacc), ptr(partner), k, d, plan.weight, pc,
-                                           ptr(gout), sp, ptr(s_c), _DTYPES[s_c.dtype], ptr(inv),
+                check(lib.mmcl_unpack_grad(h, ptr(dacc), ptr(partner), ptr(pinv), k, d, plan.weight,
+                                           pc, ptr(gout), sp, ptr(s_c), _DTYPES[s_c.dtype], ptr(inv),
                                            int(m.l2_normalize), ptr(idx), ptr(grads32[key]), st),
                       "mmcl_unpack_grad")
         out = []
@@ -514,6 +532,8 @@ class ContrastiveLoss(nn.Module):
         if not isinstance(logit_scale, torch.Tensor):
             logit_scale = torch.tensor(float(logit_scale), device=embs[0].device)
         run = _Run(self, keys, example_ids, list(modality_loss_pairs))
+        run.need_grad = torch.is_grad_enabled() and (
+            any(e.requires_grad for e in embs) or logit_scale.requires_grad)
         loss = _FusedContrastiveFn.apply(run, logit_scale, *embs)
         if not run.losses_present:
             # no loss to compute (e.g. no paired data in batch): contrastive.py:151-158

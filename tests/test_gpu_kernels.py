@@ -41,10 +41,17 @@ def test_sim_lse_fwd(nq, nk, d, s):
     es = torch.empty(nq, device=dev)
     wsb = lib.mmcl_sim_lse_workspace_bytes(h, nq, nk, d)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    check(lib.mmcl_sim_lse_fwd(h, ptr(q), nq, ptr(k), nk, d, ptr(scale), ptr(lse), ptr(es), ptr(ws),
-                               wsb, st), "fwd")
+    # un-normalised rows + fp32 inverse norms applied in the epilogue (the production path)
+    qn = (torch.rand(nq, device=dev) * 3 + 0.5)
+    kn = (torch.rand(nk, device=dev) * 3 + 0.5)
+    q = (q.float() * qn[:, None]).to(torch.bfloat16)
+    k = (k.float() * kn[:, None]).to(torch.bfloat16)
+    qinv = (1 / q.float().norm(dim=1)).contiguous()
+    kinv = (1 / k.float().norm(dim=1)).contiguous()
+    check(lib.mmcl_sim_lse_fwd(h, ptr(q), nq, ptr(k), nk, d, ptr(scale), ptr(qinv), ptr(kinv),
+                               ptr(lse), ptr(es), ptr(ws), wsb, st), "fwd")
     torch.cuda.synchronize()
-    S = s * (q.float() @ k.float().T)
+    S = s * ((q.float() * qinv[:, None]) @ (k.float() * kinv[:, None]).T)
     ref_lse = torch.logsumexp(S, dim=1)
     ref_es = (torch.softmax(S, dim=1) * S).sum(1)
     # tolerance: fp32 accumulation + ex2.approx; logits up to |s|
@@ -63,13 +70,18 @@ def test_sim_grad_bwd(nx, ny, d, s, mode):
     lib, h, dev, st = _setup()
     x, y = _rand(nx, d, dev, 3), _rand(ny, d, dev, 4)
     scale = torch.tensor([s], device=dev)
-    S = s * (x.float() @ y.float().T)
+    x = (x.float() * (torch.rand(nx, device=dev) * 3 + 0.5)[:, None]).to(torch.bfloat16)
+    y = (y.float() * (torch.rand(ny, device=dev) * 3 + 0.5)[:, None]).to(torch.bfloat16)
+    xinv = (1 / x.float().norm(dim=1)).contiguous()
+    yinv = (1 / y.float().norm(dim=1)).contiguous()
+    yh = y.float() * yinv[:, None]
+    S = s * ((x.float() * xinv[:, None]) @ yh.T)
     lse_r = torch.logsumexp(S, 1)
     lse_c = torch.logsumexp(S, 0)
     off_r = (lse_r * LOG2E + np.log2(2.0 * nx)).contiguous()
     off_c = (lse_c * LOG2E + np.log2(2.0 * ny)).contiguous()
     dx = torch.zeros(nx, d, device=dev)
-    check(lib.mmcl_sim_grad_bwd(h, ptr(x), nx, ptr(y), ny, d, ptr(scale),
+    check(lib.mmcl_sim_grad_bwd(h, ptr(x), nx, ptr(y), ny, d, ptr(scale), ptr(xinv), ptr(yinv),
                                 ptr(off_r) if mode & 1 else None, ptr(off_c) if mode & 2 else None,
                                 ptr(dx), st), "bwd")
     torch.cuda.synchronize()
@@ -78,7 +90,7 @@ def test_sim_grad_bwd(nx, ny, d, s, mode):
         G += torch.exp(S - lse_r[:, None]) / (2.0 * nx)
     if mode & 2:
         G += torch.exp(S - lse_c[None, :]) / (2.0 * ny)
-    ref = G @ y.float()
+    ref = G @ yh
     err = (dx - ref).norm() / ref.norm()
     # G is rounded to bf16 (2^-9 relative per element) before the second MMA
     assert err < 4e-3, float(err)
