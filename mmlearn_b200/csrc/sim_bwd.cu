@@ -66,6 +66,22 @@ __device__ __forceinline__ void g_chunk(const uint32_t (&v)[32], uint32_t (&g)[1
   }
 }
 
+// Fast form of MODE 3 (one ex2 per logit instead of two):
+//   2^(L-offr_i) + 2^(L-offc_j) = 2^(L-offr_i) * (1 + R_i*C_j),  R_i = 2^(offr_i-mu), C_j = 2^(mu-offc_j)
+// valid when every offset lies within +-kFastRange of mu (checked per launch, see the kernel
+// prologue); cy[e] = (C_j * yinv_j, yinv_j).
+constexpr float kFastRange = 40.f;
+__device__ __forceinline__ void g_chunk_fast(const uint32_t (&v)[32], uint32_t (&g)[16], float c,
+                                             float offr, float R, const float2* cy) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const float4 f = *reinterpret_cast<const float4*>(cy + e);  // (cyB0, yinv0, cyB1, yinv1)
+    const float e0 = ex2f(fmaf(__uint_as_float(v[e]) * f.y, c, -offr));
+    const float e1 = ex2f(fmaf(__uint_as_float(v[e + 1]) * f.w, c, -offr));
+    g[e >> 1] = pack_bf16x2(e0 * fmaf(R, f.x, f.y), e1 * fmaf(R, f.z, f.w));
+  }
+}
+
 template <bool kXRes>
 __global__ void __launch_bounds__(256, 1)
 sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY256,
@@ -82,10 +98,11 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* x_full = bars + 2 * p.nstages;
   uint64_t* x_empty = x_full + 1;
   uint64_t* s_full = x_full + 2;
-  uint64_t* g_full = x_full + 3;
-  uint64_t* acc_full = x_full + 4;
-  uint64_t* acc_empty = x_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 6);
+  uint64_t* g_full = x_full + 3;  // [2]: G of key half 0 / 1 is in tensor memory
+  uint64_t* acc_full = x_full + 5;
+  uint64_t* acc_empty = x_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 7);
+  float* s_range = reinterpret_cast<float*>(x_full + 8);  // [16] lo per warp, [16] hi per warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -100,10 +117,35 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(g_full, 128);
+    mbar_init(&g_full[0], 128);
+    mbar_init(&g_full[1], 128);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 128);
     fence_barrier_init();
+  }
+  const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
+  if (mode == 3) {
+    // range of all offsets: decides whether the one-exponential form of G is safe
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < p.nx; i += 256) {
+      const float v = p.off_row[i];
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+    for (int i = threadIdx.x; i < p.ny; i += 256) {
+      const float v = p.off_col[i];
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      s_range[warp] = lo;
+      s_range[16 + warp] = hi;
+    }
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -200,9 +242,11 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
           umma_commit(s_full);
           if (kXRes && yt == yt1 - 1) umma_commit(x_empty);
-          mbar_wait(g_full, step & 1);
-          tc_fence_after();
           for (int js = 0; js < BNY / 64; ++js) {
+            if ((js & 1) == 0) {  // G of this key half has been written to tensor memory
+              mbar_wait(&g_full[js >> 1], step & 1);
+              tc_fence_after();
+            }
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(sStage + stage * stage_bytes);
@@ -228,7 +272,18 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int et = threadIdx.x - 128;  // 0..127
     const float c0 = (*p.scale) * LOG2E;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
-    const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
+    float mu = 0.f;
+    bool fast = false;
+    if (mode == 3) {
+      float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        lo = fminf(lo, s_range[w]);
+        hi = fmaxf(hi, s_range[16 + w]);
+      }
+      mu = 0.5f * (lo + hi);
+      fast = (hi - lo) <= 2.f * kFastRange;  // false for inf/NaN ranges as well
+    }
     uint32_t step = 0, seg = 0;
     for (long long t = t_begin; t < t_end;) {
       const long long item = t / p.nyt;
@@ -239,6 +294,7 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int grow = xt * BM + row;
       const float offr = (p.off_row && grow < p.nx) ? p.off_row[grow] : INFINITY;
       const float c = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
+      const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
       for (int yt = yt0; yt < yt1; ++yt) {
         named_bar_sync(1, 128);  // everyone is done reading the previous step's column data
         for (int j = et; j < BNY; j += 128) {
@@ -246,6 +302,7 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           float2 v2;
           v2.x = (p.off_col && gy < p.ny) ? p.off_col[gy] : INFINITY;
           v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
+          if (fast) v2.x = ex2f(mu - v2.x) * v2.y;
           sCol[j] = v2;
         }
         named_bar_sync(2, 128);
@@ -256,17 +313,21 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           uint32_t v[32], g[16];
           tmem_ld_x32(tm_s + lane_base + ch * 32, v);
           tmem_ld_wait();
-          if (mode == 3)
+          if (fast)
+            g_chunk_fast(v, g, c, offr, R, sCol + ch * 32);
+          else if (mode == 3)
             g_chunk<3>(v, g, c, offr, sCol + ch * 32);
           else if (mode == 1)
             g_chunk<1>(v, g, c, offr, sCol + ch * 32);
           else
             g_chunk<2>(v, g, c, offr, sCol + ch * 32);
           tmem_st_x16(tm_s + lane_base + ch * 16, g);
+          if ((ch & 3) == 3) {  // one key half (128 columns) of G is complete
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&g_full[ch >> 2]);
+          }
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(g_full);
         ++step;
       }
       // flush this segment's accumulators
@@ -323,14 +384,14 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
   p.off_row = off_row;
   p.off_col = off_col;
   p.dx = dx;
-  const size_t budget = 227 * 1024 - 2 * BNY * sizeof(float) - 256;
+  const size_t budget = 227 * 1024 - 2 * BNY * sizeof(float) - 512;
   const bool xres = size_t(p.kchunks) * XCHUNK_BYTES + 3 * size_t(YBOX_BYTES) <= budget;
   const size_t stage_bytes = xres ? YBOX_BYTES : XCHUNK_BYTES + YBOX_BYTES;
   const size_t fixed = xres ? size_t(p.kchunks) * XCHUNK_BYTES : 0;
   int ns = int((budget - fixed) / stage_bytes);
   if (ns > 6) ns = 6;
   p.nstages = ns;
-  const size_t smem = fixed + ns * stage_bytes + 2 * BNY * sizeof(float) + 256;
+  const size_t smem = fixed + ns * stage_bytes + 2 * BNY * sizeof(float) + 512;
   CUtensorMap tmX, tmY256, tmY64;
   if (make_tmap_bf16_sw128(&tmX, x, nx, d, d, BM) ||
       make_tmap_bf16_sw128(&tmY256, y, ny, d, d, BNY) ||

@@ -98,6 +98,34 @@ def test_sim_grad_bwd(nx, ny, d, s, mode):
     assert cos > 0.9999
 
 
+def test_sim_grad_bwd_wide_offset_range():
+    """Offsets spread over more than 2*40 binades (duplicated rows at s=100): the kernel must
+    leave its one-exponential fast form and use the exact two-exponential form."""
+    from mmlearn_b200._lib import check, ptr
+
+    lib, h, dev, st = _setup()
+    nx, ny, d, s = 256, 512, 128, 100.0
+    x, y = _rand(nx, d, dev, 5), _rand(ny, d, dev, 6)
+    y[:64] = x[:64]
+    scale = torch.tensor([s], device=dev)
+    xinv = (1 / x.float().norm(dim=1)).contiguous()
+    yinv = (1 / y.float().norm(dim=1)).contiguous()
+    yh = y.float() * yinv[:, None]
+    S = s * ((x.float() * xinv[:, None]) @ yh.T)
+    lse_r, lse_c = torch.logsumexp(S, 1), torch.logsumexp(S, 0)
+    off_r = (lse_r * LOG2E + np.log2(2.0 * nx)).contiguous()
+    off_c = (lse_c * LOG2E + np.log2(2.0 * ny)).contiguous()
+    assert float(max(off_r.max(), off_c.max()) - min(off_r.min(), off_c.min())) > 80.0
+    dx = torch.zeros(nx, d, device=dev)
+    check(lib.mmcl_sim_grad_bwd(h, ptr(x), nx, ptr(y), ny, d, ptr(scale), ptr(xinv), ptr(yinv),
+                                ptr(off_r), ptr(off_c), ptr(dx), st), "bwd")
+    torch.cuda.synchronize()
+    G = torch.exp(S - lse_r[:, None]) / (2.0 * nx) + torch.exp(S - lse_c[None, :]) / (2.0 * ny)
+    ref = G @ yh
+    err = (dx - ref).norm() / ref.norm()
+    assert err < 4e-3, float(err)
+
+
 def test_match_ids_bit_exact():
     from mmlearn_b200 import find_matching_indices
     from oracle.contrastive_oracle import find_matching_indices_np, find_matching_indices_sorted
