@@ -23,6 +23,13 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
                                 const float* yinv, const float* off_row, const float* off_col,
                                 float* dx, cudaStream_t stream, const char** err);
 
+// sim_bwd_pair.cu (cudaErrorNotSupported = shape does not fit, nothing launched)
+cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
+                                     long long ny, long long d, const float* scale,
+                                     const float* xinv, const float* yinv, const float* off_row,
+                                     const float* off_col, float* dx, cudaStream_t stream,
+                                     const char** err);
+
 // aux_kernels.cu
 cudaError_t launch_pack_rows(const void* src, int src_dtype, long long src_rows, long long d,
                              const int64_t* idx, long long n_out, int normalize, void* dst_bf16,

@@ -12,6 +12,8 @@
 // Work is linearised (x-tile, d-chunk, y-tile) and cut into equal contiguous ranges, one per
 // CTA; a CTA that stops in the middle of a (x-tile, d-chunk) item adds its partial accumulator
 // into dX with fp32 reductions (red.global.add), so dX must be zero-initialised by the caller.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tma_host.h"
 #include "umma.cuh"
@@ -366,6 +368,17 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
                                 const float* yinv, const float* off_row, const float* off_col,
                                 float* dx, cudaStream_t stream, const char** err) {
   if (!off_row && !off_col) return cudaSuccess;  // G == 0
+  // CTA-pair form first (every logit tile computed once); MMCL_BWD_SINGLE=1 forces this file's
+  // single-CTA kernel (used by the tests to cover both).
+  static const bool force_single = [] {
+    const char* e = getenv("MMCL_BWD_SINGLE");
+    return e && e[0] == '1';
+  }();
+  if (!force_single) {
+    cudaError_t pe = launch_sim_grad_bwd_pair(num_sms, x, nx, y, ny, d, scale, xinv, yinv, off_row,
+                                              off_col, dx, stream, err);
+    if (pe != cudaErrorNotSupported) return pe;
+  }
   BwdParams p;
   p.nx = int(nx);
   p.ny = int(ny);

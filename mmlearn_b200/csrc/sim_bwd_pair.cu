@@ -1,0 +1,470 @@
+// Backward hot kernel, CTA-pair form (no logit recompute per d-chunk).
+//
+// Same contract as sim_bwd.cu (dX[i,:] += sum_j G[i,j] * yinv_j * Y[j,:]), but the fp32 dX
+// accumulator of a 128-row X tile -- 128 x 512 fp32 = one SM's whole tensor memory at d = 512 --
+// is split over the two CTAs of a 2-CTA cluster (two SMs): CTA c keeps the columns
+// [c*d/2, (c+1)*d/2) in tensor-memory columns [0,256) and has columns [256,512) free for one
+// 128 x 256 logit tile.  The pair walks the key tiles in lock step and ALTERNATES who recomputes
+// the logit tile: for its own step a CTA runs S = X Y^T (SS MMA, N = 256), turns S into the bf16
+// probability tile G in its epilogue warps, keeps G in tensor memory (A operand of its own
+// dX += G Y MMA, TS form) and at the same time stores G through distributed shared memory into the
+// partner's staging buffer, from where the partner feeds it to ITS dX MMA as a shared-memory A
+// operand.  Every logit tile is therefore computed exactly once per pair, and each CTA's tensor
+// pipe alternates  S(own) | dX(partner's G)  | dX(own G)  with the epilogue of S(own) hidden
+// under dX(partner's G).
+//
+// Per CTA (256 threads, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 epilogue.  Shared memory: 3 stages x 48 KB (X chunk 128x64 + Y box
+// 256x64 for S; 64-key x d/2 boxes for dX), 64 KB staging for the partner's G (K-major,
+// 128-byte swizzle, 4 atoms of 64 keys), column data, barriers.
+// Work: the (x-tile, d-pass, y-tile) space is linearised and cut into equal contiguous ranges,
+// one per pair; a range that ends inside an (x-tile, d-pass) item adds its partial accumulator
+// into dX with fp32 reductions, so dX must be zero-initialised by the caller.  d-passes exist
+// only for d > 512 (each pass covers d/ndc <= 512 columns and recomputes S).
+#include <cstdlib>
+
+#include "kernels.h"
+#include "tma_host.h"
+#include "umma.cuh"
+
+namespace mmcl {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BNY = 256;
+constexpr int BK = 64;
+constexpr int XCHUNK_BYTES = BM * BK * 2;              // 16 KB
+constexpr int YBOX_BYTES = BNY * BK * 2;               // 32 KB
+constexpr int YSUB_BYTES = 64 * BK * 2;                // 8 KB: one [64 y, 64 d] box
+constexpr int STAGE_BYTES = XCHUNK_BYTES + YBOX_BYTES; // 48 KB
+constexpr int NSTAGES = 3;
+constexpr int ATOM_BYTES = BM * 128;                   // 16 KB: 128 rows x 64 keys (bf16)
+constexpr int STG_BYTES = 4 * ATOM_BYTES;              // 64 KB: G tile 128 x 256 (bf16)
+constexpr int TAIL_BYTES = 512;                        // barriers + range scratch
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float kFastRange = 40.f;
+
+struct PairParams {
+  int nx, ny, d, kchunks;
+  int nxt, ndc, nyt;
+  int dp;   // columns per d-pass (d / ndc)
+  int dcc;  // columns per CTA (dp / 2)
+  long long total;
+  int per_pair;
+  const float* scale;
+  const float* xinv;
+  const float* yinv;
+  const float* off_row;
+  const float* off_col;
+  float* dx;
+};
+
+// exact form, see sim_bwd.cu
+template <int MODE>
+__device__ __forceinline__ void g_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float c,
+                                        float offr, const float2* cy) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const float4 f = *reinterpret_cast<const float4*>(cy + e);  // (offc0, yinv0, offc1, yinv1)
+    const float x0 = __uint_as_float(v[e]) * f.y, x1 = __uint_as_float(v[e + 1]) * f.w;
+    float g0 = 0.f, g1 = 0.f;
+    if (MODE & 1) {
+      g0 = ex2f(fmaf(x0, c, -offr));
+      g1 = ex2f(fmaf(x1, c, -offr));
+    }
+    if (MODE & 2) {
+      g0 += ex2f(fmaf(x0, c, -f.x));
+      g1 += ex2f(fmaf(x1, c, -f.z));
+    }
+    g[e >> 1] = pack_bf16x2(g0 * f.y, g1 * f.w);
+  }
+}
+// one-exponential form of MODE 3, see sim_bwd.cu
+__device__ __forceinline__ void g_chunk_fast(const uint32_t (&v)[32], uint32_t (&g)[16], float c,
+                                             float offr, float R, const float2* cy) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const float4 f = *reinterpret_cast<const float4*>(cy + e);  // (cyB0, yinv0, cyB1, yinv1)
+    const float e0 = ex2f(fmaf(__uint_as_float(v[e]) * f.y, c, -offr));
+    const float e1 = ex2f(fmaf(__uint_as_float(v[e + 1]) * f.w, c, -offr));
+    g[e >> 1] = pack_bf16x2(e0 * fmaf(R, f.x, f.y), e1 * fmaf(R, f.z, f.w));
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
+                         const __grid_constant__ CUtensorMap tmY256,
+                         const __grid_constant__ CUtensorMap tmY64, const PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* sStage = smem;
+  uint8_t* sStg = smem + NSTAGES * STAGE_BYTES;
+  float2* sCol = reinterpret_cast<float2*>(sStg + STG_BYTES);  // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + BNY);
+  uint64_t* full = bars;                  // [NSTAGES] TMA -> MMA
+  uint64_t* empty = bars + NSTAGES;       // [NSTAGES] MMA -> TMA
+  uint64_t* s_full = bars + 2 * NSTAGES;  // S tile complete in tensor memory
+  uint64_t* g_full = s_full + 1;          // [2] own G, key half 0 / 1, written to tensor memory
+  uint64_t* stg_full = s_full + 3;        // partner's G has landed in my staging buffer
+  uint64_t* stg_free = s_full + 4;        // the partner has consumed what I stored in ITS staging
+  uint64_t* acc_full = s_full + 5;
+  uint64_t* acc_empty = s_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
+  float* s_range = reinterpret_cast<float*>(s_full + 8);  // [16] lo per warp, [16] hi per warp
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = cluster_ctarank();
+  const uint32_t peer = c ^ 1u;
+  const int pair = blockIdx.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY256);
+    tma_prefetch_desc(&tmY64);
+    for (int i = 0; i < NSTAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(&g_full[0], 128);
+    mbar_init(&g_full[1], 128);
+    mbar_init(stg_full, 128);
+    mbar_init(stg_free, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_barrier_init();
+  }
+  const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
+  if (mode == 3) {
+    // range of all offsets: decides whether the one-exponential form of G is safe
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < p.nx; i += 256) {
+      const float v = p.off_row[i];
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+    for (int i = threadIdx.x; i < p.ny; i += 256) {
+      const float v = p.off_col[i];
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      s_range[warp] = lo;
+      s_range[16 + warp] = hi;
+    }
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the partner's barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_acc = tmem, tm_s = tmem + 256;
+
+  const long long t_begin = (long long)pair * p.per_pair;
+  long long t_end = t_begin + p.per_pair;
+  if (t_end > p.total) t_end = p.total;
+  const int nb = p.dcc / BK;  // 64-wide column boxes of this CTA's dX slice
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_s = [&](int xt, int yt) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* dst = sStage + stage * STAGE_BYTES;
+          tma_load_2d(dst, &tmX, kc * BK, xt * BM, &full[stage]);
+          tma_load_2d(dst + XCHUNK_BYTES, &tmY256, kc * BK, yt * BNY, &full[stage]);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+      };
+      auto load_dx = [&](int col0, int yt) {
+        for (int js = 0; js < BNY / 64; ++js) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], nb * YSUB_BYTES);
+          uint8_t* dst = sStage + stage * STAGE_BYTES;
+          for (int b = 0; b < nb; ++b)
+            tma_load_2d(dst + b * YSUB_BYTES, &tmY64, col0 + b * BK, yt * BNY + js * 64,
+                        &full[stage]);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+      };
+      bool pend = false;
+      int pend_yt = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const long long item = t / p.nyt;
+        const int yt = int(t % p.nyt);
+        const int xt = int(item / p.ndc), dc = int(item % p.ndc);
+        const int col0 = dc * p.dp + int(c) * p.dcc;
+        const bool own = (uint32_t(t - t_begin) & 1u) == c;
+        const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
+        if (own) {
+          load_s(xt, yt);
+          if (pend) { load_dx(col0, pend_yt); pend = false; }
+          load_dx(col0, yt);
+        } else {
+          pend = true;
+          pend_yt = yt;
+        }
+        if (seg_last && pend) { load_dx(col0, pend_yt); pend = false; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc_bf16(BM, BNY, 0, 0);
+      const uint32_t idesc_dx = make_idesc_bf16(BM, uint32_t(p.dcc), 0, 1);
+      const uint32_t stg = smem_u32(sStg);
+      int stage = 0;
+      uint32_t phase = 0, own_cnt = 0, peer_cnt = 0, seg = 0, accf = 0;
+      auto issue_s = [&]() {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(tm_s, make_smem_desc_sw128(st + k * 32, 0, 1024),
+                    make_smem_desc_sw128(st + XCHUNK_BYTES + k * 32, 0, 1024), idesc_s,
+                    (kc | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(s_full);
+      };
+      auto begin_dx = [&]() {
+        if (!accf) {  // the previous segment's accumulators must have been drained
+          mbar_wait(acc_empty, (seg & 1) ^ 1);
+          tc_fence_after();
+        }
+      };
+      auto issue_dx_own = [&]() {  // A = own G in tensor memory
+        begin_dx();
+        for (int js = 0; js < BNY / 64; ++js) {
+          if ((js & 1) == 0) {
+            mbar_wait(&g_full[js >> 1], own_cnt & 1);
+            tc_fence_after();
+          }
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_ts(tm_acc, tm_s + (js * 4 + k) * 8,
+                    make_smem_desc_sw128(st + k * 2048, YSUB_BYTES, 1024), idesc_dx, accf);
+            accf = 1;
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+        ++own_cnt;
+      };
+      auto issue_dx_peer = [&]() {  // A = the partner's G in my staging buffer
+        begin_dx();
+        mbar_wait_cluster(stg_full, peer_cnt & 1);
+        tc_fence_after();
+        for (int js = 0; js < BNY / 64; ++js) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_ss(tm_acc, make_smem_desc_sw128(stg + js * ATOM_BYTES + k * 32, 0, 1024),
+                    make_smem_desc_sw128(st + k * 2048, YSUB_BYTES, 1024), idesc_dx, accf);
+            accf = 1;
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+        // tell the partner's epilogue that my staging buffer may be overwritten
+        umma_commit_mcast(stg_free, uint16_t(1u << peer));
+        ++peer_cnt;
+      };
+      bool pend = false;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const int yt = int(t % p.nyt);
+        const bool own = (uint32_t(t - t_begin) & 1u) == c;
+        const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
+        if (own) {
+          issue_s();
+          if (pend) { issue_dx_peer(); pend = false; }
+          issue_dx_own();
+        } else {
+          pend = true;
+        }
+        if (seg_last) {
+          if (pend) { issue_dx_peer(); pend = false; }
+          umma_commit(acc_full);
+          accf = 0;
+          ++seg;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;  // 0..127
+    const float c0 = (*p.scale) * LOG2E;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    const uint32_t peer_stg = mapa_shared(smem_u32(sStg), peer) + uint32_t(row) * 128u;
+    const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
+    const uint32_t sw = uint32_t(row & 7);
+    float mu = 0.f;
+    bool fast = false;
+    if (mode == 3) {
+      float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        lo = fminf(lo, s_range[w]);
+        hi = fmaxf(hi, s_range[16 + w]);
+      }
+      mu = 0.5f * (lo + hi);
+      fast = (hi - lo) <= 2.f * kFastRange;  // false for inf/NaN ranges as well
+    }
+    uint32_t own_cnt = 0, seg = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const long long item = t / p.nyt;
+      const int yt = int(t % p.nyt);
+      const int xt = int(item / p.ndc), dc = int(item % p.ndc);
+      const bool own = (uint32_t(t - t_begin) & 1u) == c;
+      const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
+      const int grow = xt * BM + row;
+      if (own) {
+        const float offr = (p.off_row && grow < p.nx) ? p.off_row[grow] : INFINITY;
+        const float cc = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
+        const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
+        named_bar_sync(1, 128);  // everyone is done reading the previous step's column data
+        for (int j = et; j < BNY; j += 128) {
+          const int gy = yt * BNY + j;
+          float2 v2;
+          v2.x = (p.off_col && gy < p.ny) ? p.off_col[gy] : INFINITY;
+          v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
+          if (fast) v2.x = ex2f(mu - v2.x) * v2.y;
+          sCol[j] = v2;
+        }
+        named_bar_sync(2, 128);
+        mbar_wait(s_full, own_cnt & 1);
+        tc_fence_after();
+        // the partner has finished reading the G tile I stored two steps ago
+        mbar_wait_cluster(stg_free, (own_cnt & 1) ^ 1);
+#pragma unroll 1
+        for (int ch = 0; ch < BNY / 32; ++ch) {
+          uint32_t v[32], g[16];
+          tmem_ld_x32(tm_s + lane_base + ch * 32, v);
+          tmem_ld_wait();
+          if (fast)
+            g_chunk_fast(v, g, cc, offr, R, sCol + ch * 32);
+          else if (mode == 3)
+            g_chunk<3>(v, g, cc, offr, sCol + ch * 32);
+          else if (mode == 1)
+            g_chunk<1>(v, g, cc, offr, sCol + ch * 32);
+          else
+            g_chunk<2>(v, g, cc, offr, sCol + ch * 32);
+          tmem_st_x16(tm_s + lane_base + ch * 16, g);
+          // the same 32 keys of my row into the partner's staging tile: atom ch/2, 16-byte
+          // pieces (ch&1)*4 .. +3, XOR-swizzled with the row (128-byte swizzle, K-major)
+          const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
+          const uint32_t j0 = uint32_t(ch & 1) * 4u;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            st_cluster_v4(abase + (((j0 + qd) ^ sw) << 4), g[4 * qd], g[4 * qd + 1],
+                          g[4 * qd + 2], g[4 * qd + 3]);
+          if ((ch & 3) == 3) {  // one key half (128 columns) of G is complete
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&g_full[ch >> 2]);
+          }
+        }
+        fence_proxy_async_all();  // my DSMEM stores -> the partner's tensor-core (async) reads
+        mbar_arrive_remote(peer_stg_full);
+        ++own_cnt;
+      }
+      if (seg_last) {
+        // flush this segment's accumulators
+        mbar_wait(acc_full, seg & 1);
+        tc_fence_after();
+        const int col0 = dc * p.dp + int(c) * p.dcc;
+#pragma unroll 1
+        for (int ch = 0; ch < p.dcc / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_x32(tm_acc + lane_base + ch * 32, v);
+          tmem_ld_wait();
+          if (grow < p.nx) {
+            float* dst = p.dx + (long long)grow * p.d + col0 + ch * 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+        ++seg;
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the partner may still store into / signal this CTA
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+// Returns cudaErrorNotSupported (without launching) when the shape does not fit the pair form;
+// the caller then uses the single-CTA kernel of sim_bwd.cu.
+cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
+                                     long long ny, long long d, const float* scale,
+                                     const float* xinv, const float* yinv, const float* off_row,
+                                     const float* off_col, float* dx, cudaStream_t stream,
+                                     const char** err) {
+  if (!off_row && !off_col) return cudaSuccess;  // G == 0
+  const int ndc = int((d + 511) / 512);
+  if (num_sms < 2 || d % (128 * ndc) != 0) return cudaErrorNotSupported;
+  PairParams p;
+  p.nx = int(nx);
+  p.ny = int(ny);
+  p.d = int(d);
+  p.kchunks = int(d / BK);
+  p.nxt = int((nx + BM - 1) / BM);
+  p.ndc = ndc;
+  p.nyt = int((ny + BNY - 1) / BNY);
+  p.dp = int(d / ndc);
+  p.dcc = p.dp / 2;
+  p.total = (long long)p.nxt * p.ndc * p.nyt;
+  long long pairs = num_sms / 2;
+  if (p.total < pairs) pairs = p.total;
+  p.per_pair = int((p.total + pairs - 1) / pairs);
+  pairs = (p.total + p.per_pair - 1) / p.per_pair;
+  p.scale = scale;
+  p.xinv = xinv;
+  p.yinv = yinv;
+  p.off_row = off_row;
+  p.off_col = off_col;
+  p.dx = dx;
+  const size_t smem = size_t(NSTAGES) * STAGE_BYTES + STG_BYTES + BNY * sizeof(float2) + TAIL_BYTES;
+  CUtensorMap tmX, tmY256, tmY64;
+  if (make_tmap_bf16_sw128(&tmX, x, nx, d, d, BM) ||
+      make_tmap_bf16_sw128(&tmY256, y, ny, d, d, BNY) ||
+      make_tmap_bf16_sw128(&tmY64, y, ny, d, d, 64)) {
+    *err = "sim_grad_bwd_pair: cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaFuncSetAttribute(sim_grad_bwd_pair_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  sim_grad_bwd_pair_kernel<<<int(2 * pairs), 256, smem, stream>>>(tmX, tmY256, tmY64, p);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
+}  // namespace mmcl
