@@ -129,7 +129,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     mbar_init(s_full, 1);
     mbar_init(&g_full[0], 128);
     mbar_init(&g_full[1], 128);
-    mbar_init(stg_full, 128);
+    mbar_init(stg_full, 1);  // armed with expect_tx by the MMA issuer; bytes arrive via st.async
     mbar_init(stg_free, 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 128);
@@ -270,7 +270,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
       };
       auto issue_dx_peer = [&]() {  // A = the partner's G in my staging buffer
         begin_dx();
+        mbar_arrive_expect_tx(stg_full, STG_BYTES);  // 128 rows x 512 B from the partner's st.async
         mbar_wait_cluster(stg_full, peer_cnt & 1);
+        fence_proxy_async_smem();  // the partner's stores -> my tensor-core (async proxy) reads
         tc_fence_after();
         for (int js = 0; js < BNY / 64; ++js) {
           mbar_wait(&full[stage], phase);
@@ -377,16 +379,14 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           const uint32_t j0 = uint32_t(ch & 1) * 4u;
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd)
-            st_cluster_v4(abase + (((j0 + qd) ^ sw) << 4), g[4 * qd], g[4 * qd + 1],
-                          g[4 * qd + 2], g[4 * qd + 3]);
+            st_async_v4(abase + (((j0 + qd) ^ sw) << 4), g[4 * qd], g[4 * qd + 1], g[4 * qd + 2],
+                        g[4 * qd + 3], peer_stg_full);
           if ((ch & 3) == 3) {  // one key half (128 columns) of G is complete
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&g_full[ch >> 2]);
           }
         }
-        fence_proxy_async_all();  // my DSMEM stores -> the partner's tensor-core (async) reads
-        mbar_arrive_remote(peer_stg_full);
         ++own_cnt;
       }
       if (seg_last) {

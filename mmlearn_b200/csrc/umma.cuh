@@ -342,6 +342,16 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
                "r"(b), "r"(c), "r"(d)
                : "memory");
 }
+// asynchronous 16-byte store into a (peer) CTA's shared memory; completes 16 tx-bytes on the
+// mbarrier at `cluster_mbar` (same CTA as the destination).  No fence needed by the writer.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b,
+                                            uint32_t c, uint32_t d, uint32_t cluster_mbar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, "
+      "[%5];" ::"r"(cluster_addr),
+      "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_mbar)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
