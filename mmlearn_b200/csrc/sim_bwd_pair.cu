@@ -13,8 +13,10 @@
 // pipe alternates  S(own) | dX(partner's G)  | dX(own G)  with the epilogue of S(own) hidden
 // under dX(partner's G).
 //
-// Per CTA (256 threads, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue.  Shared memory: 3 stages x 48 KB (X chunk 128x64 + Y box
+// Per CTA (384 threads, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 epilogue of key half 0 (S columns 0-127), warps 8-11 epilogue of key half 1
+// (two warps per SM sub-partition hide the tensor-memory load latency; the ex2 rate of 16/clk/SM
+// is the floor of the epilogue).  Shared memory: 3 stages x 48 KB (X chunk 128x64 + Y box
 // 256x64 for S; 64-key x d/2 boxes for dX), 64 KB staging for the partner's G (K-major,
 // 128-byte swizzle, 4 atoms of 64 keys), column data, barriers.
 // Work: the (x-tile, d-pass, y-tile) space is linearised and cut into equal contiguous ranges,
@@ -41,9 +43,29 @@ constexpr int STAGE_BYTES = XCHUNK_BYTES + YBOX_BYTES; // 48 KB
 constexpr int NSTAGES = 3;
 constexpr int ATOM_BYTES = BM * 128;                   // 16 KB: 128 rows x 64 keys (bf16)
 constexpr int STG_BYTES = 4 * ATOM_BYTES;              // 64 KB: G tile 128 x 256 (bf16)
+constexpr int XFER_BYTES = 8 * 2048;                   // per epilogue warp: 32 rows x 64 B
 constexpr int TAIL_BYTES = 512;                        // barriers + range scratch
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float kFastRange = 40.f;
+
+#ifdef MMCL_TRACE
+// timeline instrumentation (tools/bwd_trace.cu): (event, step, globaltimer ns) for pair 0
+__device__ unsigned long long g_trace[2][4096][2];
+__device__ unsigned int g_trace_n[2];
+__device__ __forceinline__ void trace_ev(int pair, uint32_t cta, unsigned ev, unsigned step) {
+  if (pair != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned i = atomicAdd(&g_trace_n[cta], 1u);
+  if (i < 4096) {
+    g_trace[cta][i][0] = (static_cast<unsigned long long>(ev) << 32) | step;
+    g_trace[cta][i][1] = t;
+  }
+}
+#define TRACE(ev, step) trace_ev(pair, c, ev, unsigned(step))
+#else
+#define TRACE(ev, step)
+#endif
 
 struct PairParams {
   int nx, ny, d, kchunks;
@@ -92,7 +114,9 @@ __device__ __forceinline__ void g_chunk_fast(const uint32_t (&v)[32], uint32_t (
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+constexpr int NTHREADS = 384;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
                          const __grid_constant__ CUtensorMap tmY256,
                          const __grid_constant__ CUtensorMap tmY64, const PairParams p) {
@@ -101,7 +125,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
   uint8_t* sStage = smem;
   uint8_t* sStg = smem + NSTAGES * STAGE_BYTES;
   float2* sCol = reinterpret_cast<float2*>(sStg + STG_BYTES);  // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + BNY);
+  uint8_t* sXfer = reinterpret_cast<uint8_t*>(sCol + BNY);  // [8 warps][2 KB] transposition
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXfer + XFER_BYTES);
   uint64_t* full = bars;                  // [NSTAGES] TMA -> MMA
   uint64_t* empty = bars + NSTAGES;       // [NSTAGES] MMA -> TMA
   uint64_t* s_full = bars + 2 * NSTAGES;  // S tile complete in tensor memory
@@ -132,19 +157,19 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     mbar_init(stg_full, 1);  // armed with expect_tx by the MMA issuer; bytes arrive via st.async
     mbar_init(stg_free, 1);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, 256);
     fence_barrier_init();
   }
   const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
   if (mode == 3) {
     // range of all offsets: decides whether the one-exponential form of G is safe
     float lo = INFINITY, hi = -INFINITY;
-    for (int i = threadIdx.x; i < p.nx; i += 256) {
+    for (int i = threadIdx.x; i < p.nx; i += NTHREADS) {
       const float v = p.off_row[i];
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
-    for (int i = threadIdx.x; i < p.ny; i += 256) {
+    for (int i = threadIdx.x; i < p.ny; i += NTHREADS) {
       const float v = p.off_col[i];
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
@@ -227,6 +252,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
       int stage = 0;
       uint32_t phase = 0, own_cnt = 0, peer_cnt = 0, seg = 0, accf = 0;
       auto issue_s = [&]() {
+        TRACE(0, own_cnt);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -240,6 +266,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(s_full);
+        TRACE(1, own_cnt);
       };
       auto begin_dx = [&]() {
         if (!accf) {  // the previous segment's accumulators must have been drained
@@ -253,25 +280,33 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           if ((js & 1) == 0) {
             mbar_wait(&g_full[js >> 1], own_cnt & 1);
             tc_fence_after();
+            TRACE(5 + (js >> 1), own_cnt);
           }
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_ts(tm_acc, tm_s + (js * 4 + k) * 8,
+            umma_ts(tm_acc, tm_s + (js >> 1) * 128 + (js & 1) * 32 + k * 8,
                     make_smem_desc_sw128(st + k * 2048, YSUB_BYTES, 1024), idesc_dx, accf);
             accf = 1;
           }
           umma_commit(&empty[stage]);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
+        TRACE(7, own_cnt);
         ++own_cnt;
       };
       auto issue_dx_peer = [&]() {  // A = the partner's G in my staging buffer
         begin_dx();
+        TRACE(2, peer_cnt);
+#ifdef MMCL_NO_DSM  // timing experiment only (tools/bwd_trace.cu): no G exchange, wrong results
+        mbar_arrive_expect_tx(stg_full, 2 * 8 * 8 * 16);
+#else
         mbar_arrive_expect_tx(stg_full, STG_BYTES);  // 128 rows x 512 B from the partner's st.async
+#endif
         mbar_wait_cluster(stg_full, peer_cnt & 1);
+        TRACE(3, peer_cnt);
         fence_proxy_async_smem();  // the partner's stores -> my tensor-core (async proxy) reads
         tc_fence_after();
         for (int js = 0; js < BNY / 64; ++js) {
@@ -289,6 +324,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         }
         // tell the partner's epilogue that my staging buffer may be overwritten
         umma_commit_mcast(stg_free, uint16_t(1u << peer));
+        TRACE(4, peer_cnt);
         ++peer_cnt;
       };
       bool pend = false;
@@ -313,12 +349,14 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
-    const int q = warp - 4;
+    const int wg = (warp - 4) >> 2;  // key half this warpgroup converts
+    const int q = warp & 3;          // TMEM lane quadrant (== warp % 4)
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..127
+    const int et = threadIdx.x - 128 - wg * 128;  // 0..127 within the warpgroup
     const float c0 = (*p.scale) * LOG2E;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
-    const uint32_t peer_stg = mapa_shared(smem_u32(sStg), peer) + uint32_t(row) * 128u;
+    const uint32_t peer_stg = mapa_shared(smem_u32(sStg), peer) + uint32_t(q * 32) * 128u;
+    const uint32_t xb = smem_u32(sXfer) + uint32_t(warp - 4) * 2048u;
     const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
     const uint32_t sw = uint32_t(row & 7);
     float mu = 0.f;
@@ -326,7 +364,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     if (mode == 3) {
       float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < NTHREADS / 32; ++w) {
         lo = fminf(lo, s_range[w]);
         hi = fmaxf(hi, s_range[16 + w]);
       }
@@ -345,8 +383,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         const float offr = (p.off_row && grow < p.nx) ? p.off_row[grow] : INFINITY;
         const float cc = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
         const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
-        named_bar_sync(1, 128);  // everyone is done reading the previous step's column data
-        for (int j = et; j < BNY; j += 128) {
+        named_bar_sync(1 + 2 * wg, 128);  // the warpgroup is done with the previous column data
+        {
+          const int j = wg * 128 + et;
           const int gy = yt * BNY + j;
           float2 v2;
           v2.x = (p.off_col && gy < p.ny) ? p.off_col[gy] : INFINITY;
@@ -354,13 +393,16 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           if (fast) v2.x = ex2f(mu - v2.x) * v2.y;
           sCol[j] = v2;
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2 + 2 * wg, 128);
         mbar_wait(s_full, own_cnt & 1);
         tc_fence_after();
-        // the partner has finished reading the G tile I stored two steps ago
-        mbar_wait_cluster(stg_free, (own_cnt & 1) ^ 1);
+        if (lane == 0 && q == 0) TRACE(10 + wg, own_cnt);
+        // the partner has finished reading the G tile I stored two steps ago (write-after-read
+        // on its staging buffer; nothing is read here, so CTA-scope acquire is enough)
+        mbar_wait(stg_free, (own_cnt & 1) ^ 1);
+        if (lane == 0 && q == 0) TRACE(12 + wg, own_cnt);
 #pragma unroll 1
-        for (int ch = 0; ch < BNY / 32; ++ch) {
+        for (int ch = wg * 4; ch < wg * 4 + 4; ++ch) {
           uint32_t v[32], g[16];
           tmem_ld_x32(tm_s + lane_base + ch * 32, v);
           tmem_ld_wait();
@@ -372,21 +414,44 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
             g_chunk<1>(v, g, cc, offr, sCol + ch * 32);
           else
             g_chunk<2>(v, g, cc, offr, sCol + ch * 32);
-          tmem_st_x16(tm_s + lane_base + ch * 16, g);
-          // the same 32 keys of my row into the partner's staging tile: atom ch/2, 16-byte
-          // pieces (ch&1)*4 .. +3, XOR-swizzled with the row (128-byte swizzle, K-major)
-          const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
+          // G of key half h lives in S columns [128 h, 128 h + 64): inside the columns this
+          // warpgroup has already consumed
+          tmem_st_x16(tm_s + lane_base + wg * 128 + (ch & 3) * 16, g);
+          // The same 32 keys (64 B per row) go to the partner's staging tile (atom ch/2, 128-byte
+          // swizzle, K-major).  Distributed-shared-memory stores are packet-rate bound, so the
+          // warp first transposes through a 2 KB buffer: each st.async instruction then covers
+          // 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
           const uint32_t j0 = uint32_t(ch & 1) * 4u;
+          __syncwarp();  // the previous chunk has been read out of the buffer
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-            st_async_v4(abase + (((j0 + qd) ^ sw) << 4), g[4 * qd], g[4 * qd + 1], g[4 * qd + 2],
-                        g[4 * qd + 3], peer_stg_full);
-          if ((ch & 3) == 3) {  // one key half (128 columns) of G is complete
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&g_full[ch >> 2]);
+          for (int qd = 0; qd < 4; ++qd) {
+            const uint32_t a = xb + uint32_t(lane) * 64u + ((((j0 + qd) ^ sw) & 3u) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(g[4 * qd]),
+                         "r"(g[4 * qd + 1]), "r"(g[4 * qd + 2]), "r"(g[4 * qd + 3])
+                         : "memory");
+          }
+          __syncwarp();
+          const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
+#pragma unroll
+          for (int s2 = 0; s2 < 4; ++s2) {
+            const uint32_t r = uint32_t(s2 * 8 + (lane >> 2));  // row within the warp's 32 rows
+            const uint32_t half = (uint32_t(ch) ^ (r >> 2)) & 1u;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(xb + uint32_t(s2 * 512 + lane * 16))
+                         : "memory");
+#ifdef MMCL_NO_DSM
+            if (s2 == 0 && (ch & 3) == 0 && lane < 8)  // 64 x 16 B... timing experiment only
+#endif
+            st_async_v4(abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4), w0, w1, w2, w3,
+                        peer_stg_full);
           }
         }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&g_full[wg]);  // this key half (128 columns) of G is complete
+        if (lane == 0 && q == 0) TRACE(14 + wg, own_cnt);
         ++own_cnt;
       }
       if (seg_last) {
@@ -395,7 +460,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         tc_fence_after();
         const int col0 = dc * p.dp + int(c) * p.dcc;
 #pragma unroll 1
-        for (int ch = 0; ch < p.dcc / 32; ++ch) {
+        for (int ch = wg; ch < p.dcc / 32; ch += 2) {
           uint32_t v[32];
           tmem_ld_x32(tm_acc + lane_base + ch * 32, v);
           tmem_ld_wait();
@@ -451,7 +516,8 @@ cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, c
   p.off_row = off_row;
   p.off_col = off_col;
   p.dx = dx;
-  const size_t smem = size_t(NSTAGES) * STAGE_BYTES + STG_BYTES + BNY * sizeof(float2) + TAIL_BYTES;
+  const size_t smem =
+      size_t(NSTAGES) * STAGE_BYTES + STG_BYTES + BNY * sizeof(float2) + XFER_BYTES + TAIL_BYTES;
   CUtensorMap tmX, tmY256, tmY64;
   if (make_tmap_bf16_sw128(&tmX, x, nx, d, d, BM) ||
       make_tmap_bf16_sw128(&tmY256, y, ny, d, d, BNY) ||
@@ -462,7 +528,7 @@ cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, c
   cudaError_t e = cudaFuncSetAttribute(sim_grad_bwd_pair_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  sim_grad_bwd_pair_kernel<<<int(2 * pairs), 256, smem, stream>>>(tmX, tmY256, tmY64, p);
+  sim_grad_bwd_pair_kernel<<<int(2 * pairs), NTHREADS, smem, stream>>>(tmX, tmY256, tmY64, p);
   count_launches(1);
   return cudaGetLastError();
 }
