@@ -154,7 +154,9 @@ int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* 
  *   g_hat[i,:] = coef * ( dacc[i,:] - pos_coef * partner_inv[i] * partner[i,:] )
  *                                                                       coef = weight*(*gout)*(*s)
  *   g[i,:]     = normalise-backward(g_hat[i,:]; src row, inv_norm[i])  (if normalize)
- *   grad[idx[i],:] += g[i,:]                                           (fp32 atomics)
+ *   direct == 0:  grad[idx[i],:] += g[i,:]   fp32 atomics; grad is fp32 (grad_dtype MMCL_F32)
+ *   direct == 1:  grad[i,:]       = g[i,:]   plain stores in grad_dtype; idx must be NULL (the
+ *                 identity row map) and this must be the only contribution to those rows
  * Replaces: backward of index-select (index_put accumulate), of F.normalize and the
  * positive-label term of cross_entropy's backward.
  * ------------------------------------------------------------------------------------------ */
@@ -162,7 +164,8 @@ int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16
                      const float* partner_inv, int64_t n,
                      int64_t d, double weight, double pos_coef, const float* gout,
                      const float* scale, const void* src, int src_dtype, const float* inv_norm,
-                     int normalize, const int64_t* idx, float* grad_f32, mmcl_stream stream);
+                     int normalize, const int64_t* idx, void* grad, int grad_dtype, int direct,
+                     mmcl_stream stream);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,7 @@ SYMBOLS = {
                                   c_void_p]),
     "mmcl_unpack_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
                                  c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                 c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 NCCL_UID_BYTES = 128

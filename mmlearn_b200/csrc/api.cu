@@ -350,18 +350,21 @@ int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16
                      const float* partner_inv, int64_t n,
                      int64_t d, double weight, double pos_coef, const float* gout,
                      const float* scale, const void* src, int src_dtype, const float* inv_norm,
-                     int normalize, const int64_t* idx, float* grad_f32, mmcl_stream stream) {
+                     int normalize, const int64_t* idx, void* grad, int grad_dtype, int direct,
+                     mmcl_stream stream) {
   REQUIRE(h && scale, "mmcl_unpack_grad: null handle/scale");
   REQUIRE(n >= 0 && d > 0 && d % 8 == 0 && d <= 2048, "mmcl_unpack_grad: bad n/d");
   REQUIRE(src_dtype >= 0 && src_dtype <= 2, "mmcl_unpack_grad: dtype must be f32/bf16/f16");
-  REQUIRE(n == 0 || (dacc && partner_bf16 && grad_f32), "mmcl_unpack_grad: null buffer");
+  REQUIRE(grad_dtype >= 0 && grad_dtype <= 2, "mmcl_unpack_grad: grad dtype must be f32/bf16/f16");
+  REQUIRE(direct || grad_dtype == MMCL_F32, "mmcl_unpack_grad: accumulation needs an fp32 buffer");
+  REQUIRE(!direct || !idx, "mmcl_unpack_grad: direct stores need the identity row map");
+  REQUIRE(n == 0 || (dacc && partner_bf16 && grad), "mmcl_unpack_grad: null buffer");
   REQUIRE(!normalize || (src && inv_norm), "mmcl_unpack_grad: normalize needs src and inv_norm");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaError_t e = launch_unpack_grad(dacc, partner_bf16, partner_inv, n, d, weight, pos_coef, gout,
-                                     scale, src,
-                                     src_dtype, inv_norm, normalize, idx, grad_f32,
-                                     static_cast<cudaStream_t>(stream));
+                                     scale, src, src_dtype, inv_norm, normalize, idx, grad,
+                                     grad_dtype, direct, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_unpack_grad");
 }
 

@@ -116,16 +116,34 @@ __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long
   }
 }
 
-__global__ void pair_loss_kernel(const float* __restrict__ lse_a, const float* __restrict__ lse_b,
+__global__ void __launch_bounds__(512)
+pair_loss_kernel(const float* __restrict__ lse_a, const float* __restrict__ lse_b,
                                  const float* __restrict__ esum_a, const float* __restrict__ esum_b,
                                  const float* __restrict__ pos, long long n, double coef,
                                  const float* __restrict__ scale, float* __restrict__ out2) {
+  // one block (fixed summation order => bit-reproducible loss); 8 independent loads per array
+  // in flight per thread
   __shared__ double sh[2][32];
   double l = 0.0, e = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const double p2 = 2.0 * (double)pos[i];
-    l += (double)lse_a[i] + (double)lse_b[i] - p2;
-    e += (double)esum_a[i] + (double)esum_b[i] - p2;
+  constexpr int U = 8;
+  for (long long base = 0; base < n; base += (long long)blockDim.x * U) {
+    float la[U], lb[U], ea[U], eb[U], pp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + (long long)u * blockDim.x + threadIdx.x;
+      const bool ok = i < n;
+      la[u] = ok ? lse_a[i] : 0.f;
+      lb[u] = ok ? lse_b[i] : 0.f;
+      ea[u] = ok ? esum_a[i] : 0.f;
+      eb[u] = ok ? esum_b[i] : 0.f;
+      pp[u] = ok ? pos[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double p2 = 2.0 * (double)pp[u];
+      l += (double)la[u] + (double)lb[u] - p2;
+      e += (double)ea[u] + (double)eb[u] - p2;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -159,14 +177,41 @@ __global__ void make_offsets_kernel(const float* __restrict__ lse, long long n,
   off[i] = fmaf(lse[i], LOG2E, dl);
 }
 
-template <int DT>
+// store 8 consecutive fp32 values as dtype ODT (0 f32, 1 bf16, 2 f16)
+template <int ODT>
+__device__ __forceinline__ void store8(void* base, long long elem, const float (&o)[8]) {
+  if (ODT == 0) {
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + elem);
+    p[0] = make_float4(o[0], o[1], o[2], o[3]);
+    p[1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else if (ODT == 1) {
+    uint4 u;
+    u.x = bf16x2(o[0], o[1]);
+    u.y = bf16x2(o[2], o[3]);
+    u.z = bf16x2(o[4], o[5]);
+    u.w = bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + elem) = u;
+  } else {
+    uint4 u;
+    __half2 h;
+    h = __floats2half2_rn(o[0], o[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(o[2], o[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(o[4], o[5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(o[6], o[7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(static_cast<__half*>(base) + elem) = u;
+  }
+}
+
+// kDirect: idx == identity and this is the only contribution to the rows -> plain stores in the
+// output dtype ODT; otherwise fp32 atomics into `grad` (ODT == 0).
+template <int DT, int ODT, bool kDirect>
 __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
                                    const __nv_bfloat16* __restrict__ partner,
                                    const float* __restrict__ partner_inv, long long n, int d,
                                    float weight, float pos_coef, const float* __restrict__ gout,
                                    const float* __restrict__ scale, const void* __restrict__ src,
                                    const float* __restrict__ inv_norm, int normalize,
-                                   const int64_t* __restrict__ idx, float* __restrict__ grad) {
+                                   const int64_t* __restrict__ idx, void* __restrict__ grad) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -174,43 +219,51 @@ __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
   const long long srow = idx ? idx[row] : row;
   constexpr int MAXV = 8;  // supports d <= 2048 with the register-resident path
   float g[MAXV][8];
+  float x[MAXV][8];
   float dot = 0.f;
   const float inv = normalize ? inv_norm[row] : 1.f;
   const float pc = pos_coef * (partner_inv ? partner_inv[row] : 1.f);
-  int nv = 0;
-  for (int c = lane * 8; c < d; c += 256, ++nv) {
-    float pa[8];
-    const float4 a0 = *reinterpret_cast<const float4*>(dacc + row * d + c);
-    const float4 a1 = *reinterpret_cast<const float4*>(dacc + row * d + c + 4);
-    load8<1>(partner, row * d + c, pa);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pc * pa[i]);
-    if (normalize) {
-      float x[8];
-      load8<DT>(src, srow * d + c, x);
+  for (int nv = 0; nv < MAXV; ++nv) {
+    const int c = lane * 8 + nv * 256;
+    if (c < d) {
+      float pa[8];
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(dacc + row * d + c));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(dacc + row * d + c + 4));
+      load8<1>(partner, row * d + c, pa);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[i] * inv, dot);
+      for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pc * pa[i]);
+      if (normalize) {
+        load8<DT>(src, srow * d + c, x[nv]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[nv][i] * inv, dot);
+      }
     }
   }
   if (normalize) dot = warp_sum(dot);
   const bool clamped = inv >= 0.99e12f;  // ||x|| < eps: x_hat = x / eps, a plain scaling
-  nv = 0;
-  for (int c = lane * 8; c < d; c += 256, ++nv) {
-    float o[8];
-    if (normalize) {
-      float x[8];
-      load8<DT>(src, srow * d + c, x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o[i] = clamped ? g[nv][i] * inv : inv * (g[nv][i] - x[i] * inv * dot);
-    } else {
+  for (int nv = 0; nv < MAXV; ++nv) {
+    const int c = lane * 8 + nv * 256;
+    if (c < d) {
+      float o[8];
+      if (normalize) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = g[nv][i];
+        for (int i = 0; i < 8; ++i)
+          o[i] = clamped ? g[nv][i] * inv : inv * (g[nv][i] - x[nv][i] * inv * dot);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = g[nv][i];
+      }
+      if (kDirect) {
+        store8<ODT>(grad, srow * d + c, o);
+      } else {
+        float* dst = static_cast<float*>(grad) + srow * d + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, o[i]);
+      }
     }
-    float* dst = grad + srow * d + c;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, o[i]);
   }
 }
 
@@ -250,7 +303,7 @@ cudaError_t launch_pair_loss(const float* lse_a, const float* lse_b, const float
                              const float* esum_b, const float* pos, long long n, double weight,
                              double n_norm, const float* scale, float* out2, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  pair_loss_kernel<<<1, 1024, 0, stream>>>(lse_a, lse_b, esum_a, esum_b, pos, n,
+  pair_loss_kernel<<<1, 512, 0, stream>>>(lse_a, lse_b, esum_a, esum_b, pos, n,
                                            weight / (2.0 * n_norm), scale, out2);
   count_launches(1);
   return cudaGetLastError();
@@ -270,17 +323,32 @@ cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16,
                                long long d, double weight, double pos_coef, const float* gout,
                                const float* scale, const void* src, int src_dtype,
                                const float* inv_norm, int normalize, const int64_t* idx,
-                               float* grad_f32, cudaStream_t stream) {
+                               void* grad, int grad_dtype, int direct, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   const int wpb = 4;
   const unsigned blocks = unsigned((n + wpb - 1) / wpb);
   auto* pb = static_cast<const __nv_bfloat16*>(partner_bf16);
-  if (src_dtype == 0)
-    unpack_grad_kernel<0><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
-  else if (src_dtype == 1)
-    unpack_grad_kernel<1><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
-  else
-    unpack_grad_kernel<2><<<blocks, wpb * 32, 0, stream>>>(dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src, inv_norm, normalize, idx, grad_f32);
+#define MMCL_UNPACK(DT, ODT, DIRECT)                                                              \
+  unpack_grad_kernel<DT, ODT, DIRECT><<<blocks, wpb * 32, 0, stream>>>(                           \
+      dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src,         \
+      inv_norm, normalize, idx, grad)
+#define MMCL_UNPACK_SRC(ODT, DIRECT)                                                              \
+  do {                                                                                            \
+    if (src_dtype == 0) MMCL_UNPACK(0, ODT, DIRECT);                                              \
+    else if (src_dtype == 1) MMCL_UNPACK(1, ODT, DIRECT);                                         \
+    else MMCL_UNPACK(2, ODT, DIRECT);                                                             \
+  } while (0)
+  if (!direct) {
+    MMCL_UNPACK_SRC(0, false);
+  } else if (grad_dtype == 0) {
+    MMCL_UNPACK_SRC(0, true);
+  } else if (grad_dtype == 1) {
+    MMCL_UNPACK_SRC(1, true);
+  } else {
+    MMCL_UNPACK_SRC(2, true);
+  }
+#undef MMCL_UNPACK_SRC
+#undef MMCL_UNPACK
   count_launches(1);
   return cudaGetLastError();
 }

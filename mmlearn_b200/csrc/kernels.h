@@ -48,7 +48,7 @@ cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16,
                                long long d, double weight, double pos_coef, const float* gout,
                                const float* scale, const void* src, int src_dtype,
                                const float* inv_norm, int normalize, const int64_t* idx,
-                               float* grad_f32, cudaStream_t stream);
+                               void* grad, int grad_dtype, int direct, cudaStream_t stream);
 
 // match.cu
 size_t match_workspace_bytes(long long n, long long m);

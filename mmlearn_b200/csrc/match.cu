@@ -21,8 +21,13 @@ struct MatchWs {
   int* cnt_a;        // [n]
   int* slot_a;       // [n]
   long long* off_a;  // [n] exclusive scan of cnt_a
+  long long* bsum;   // [max(T, n) / SCAN_TILE + 1] per-tile sums of the running scan
   long long T;
 };
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;  // 2048 elements per block
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
@@ -50,6 +55,7 @@ size_t carve(MatchWs* w, void* base, long long n, long long m) {
   w->cnt_a = static_cast<int*>(take(n * 4));
   w->slot_a = static_cast<int*>(take(n * 4));
   w->off_a = static_cast<long long*>(take(n * 8));
+  w->bsum = static_cast<long long*>(take(((T > n ? T : n) / SCAN_TILE + 1) * 8));
   return o;
 }
 
@@ -88,29 +94,92 @@ __global__ void insert_kernel(MatchWs w, const long long* __restrict__ ids_b, lo
   }
 }
 
-// single-block exclusive scan, int -> long long; writes the total to *total if non-null
-__global__ void scan_kernel(const int* __restrict__ in, long long* __restrict__ out, long long n,
-                            long long* total) {
-  __shared__ long long part[1024];
-  const int t = threadIdx.x;
-  const long long per = (n + blockDim.x - 1) / blockDim.x;
-  const long long lo = t * per, hi = lo + per < n ? lo + per : n;
+// Exclusive scan int -> long long in three small launches: per-tile sums, scan of the tile sums
+// (one block), per-tile scan with the tile offset.  Tiles are read with coalesced accesses.
+__global__ void scan_tile_sums_kernel(const int* __restrict__ in, long long n,
+                                      long long* __restrict__ bsum) {
+  __shared__ long long wsum[SCAN_THREADS / 32];
+  const long long base = (long long)blockIdx.x * SCAN_TILE;
   long long s = 0;
-  for (long long i = lo; i < hi; ++i) s += in[i];
-  part[t] = s;
+#pragma unroll
+  for (int e = 0; e < SCAN_PER_THREAD; ++e) {
+    const long long i = base + e * SCAN_THREADS + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
   __syncthreads();
-  for (int o = 1; o < blockDim.x; o <<= 1) {
-    long long v = t >= o ? part[t - o] : 0;
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) t += wsum[w];
+    bsum[blockIdx.x] = t;
+  }
+}
+
+// one block: bsum[0..nb) -> exclusive scan in place; *total = sum
+__global__ void scan_bsums_kernel(long long* __restrict__ bsum, long long nb,
+                                  long long* __restrict__ total) {
+  __shared__ long long part[1024];
+  __shared__ long long carry_s;
+  const int t = threadIdx.x;
+  if (t == 0) carry_s = 0;
+  __syncthreads();
+  for (long long base = 0; base < nb; base += 1024) {
+    const long long i = base + t;
+    const long long v = i < nb ? bsum[i] : 0;
+    part[t] = v;
     __syncthreads();
-    part[t] += v;
+    for (int o = 1; o < 1024; o <<= 1) {
+      const long long a = t >= o ? part[t - o] : 0;
+      __syncthreads();
+      part[t] += a;
+      __syncthreads();
+    }
+    const long long carry = carry_s;
+    if (i < nb) bsum[i] = carry + part[t] - v;
+    __syncthreads();
+    if (t == 1023) carry_s = carry + part[t];
     __syncthreads();
   }
-  long long run = part[t] - s;
-  for (long long i = lo; i < hi; ++i) {
-    out[i] = run;
-    run += in[i];
+  if (total && t == 0) *total = carry_s;
+}
+
+__global__ void scan_tiles_kernel(const int* __restrict__ in, long long* __restrict__ out,
+                                  long long n, const long long* __restrict__ bsum) {
+  __shared__ long long wsum[SCAN_THREADS / 32];
+  // thread t owns the SCAN_PER_THREAD consecutive elements [base + t*P, base + (t+1)*P)
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
+  int v[SCAN_PER_THREAD];
+  long long s = 0;
+#pragma unroll
+  for (int e = 0; e < SCAN_PER_THREAD; ++e) {
+    v[e] = base + e < n ? in[base + e] : 0;
+    s += v[e];
   }
-  if (total && t == blockDim.x - 1) *total = part[t];
+  long long incl = s;  // inclusive scan of the per-thread sums across the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long a = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += a;
+  }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  long long run = bsum[blockIdx.x] + incl - s;
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) run += wsum[w];
+#pragma unroll
+  for (int e = 0; e < SCAN_PER_THREAD; ++e) {
+    if (base + e < n) out[base + e] = run;
+    run += v[e];
+  }
+}
+
+void launch_scan(const int* in, long long* out, long long n, long long* total, long long* bsum,
+                 cudaStream_t stream) {
+  const long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  scan_tile_sums_kernel<<<unsigned(nb), SCAN_THREADS, 0, stream>>>(in, n, bsum);
+  scan_bsums_kernel<<<1, 1024, 0, stream>>>(bsum, nb, total);
+  scan_tiles_kernel<<<unsigned(nb), SCAN_THREADS, 0, stream>>>(in, out, n, bsum);
 }
 
 __global__ void fill_kernel(MatchWs w, long long m) {
@@ -208,14 +277,14 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
   const auto* b = reinterpret_cast<const long long*>(ids_b);
   init_kernel<<<blocks(w.T), B, 0, stream>>>(w);
   insert_kernel<<<blocks(m), B, 0, stream>>>(w, b, m);
-  scan_kernel<<<1, 1024, 0, stream>>>(w.count, w.start, w.T, nullptr);
+  launch_scan(w.count, w.start, w.T, nullptr, w.bsum, stream);
   fill_kernel<<<blocks(m), B, 0, stream>>>(w, m);
   sort_buckets_kernel<<<blocks(w.T), B, 0, stream>>>(w);
   lookup_kernel<<<blocks(n), B, 0, stream>>>(w, a, n, b);
-  scan_kernel<<<1, 1024, 0, stream>>>(w.cnt_a, w.off_a, n, info);
+  launch_scan(w.cnt_a, w.off_a, n, info, w.bsum, stream);
   emit_kernel<<<blocks(n), B, 0, stream>>>(w, n, m, reinterpret_cast<long long*>(out_a),
                                            reinterpret_cast<long long*>(out_b), capacity, info);
-  count_launches(8);
+  count_launches(12);
   return cudaGetLastError();
 }
 

@@ -379,6 +379,14 @@ class _Run:
         m = self.m
         gout = gout.detach().to(device=dev, dtype=torch.float32).contiguous()
         grads32: dict = {}
+        direct: dict = {}
+        # how many (pair, side) terms feed each embedding tensor: a tensor fed by exactly one
+        # term through the identity row map gets its gradient written once, in its own dtype
+        n_terms: dict = {}
+        for stt in self.states:
+            if stt.plan.b_local > 0:
+                for key in (stt.key_a, stt.key_b):
+                    n_terms[key] = n_terms.get(key, 0) + 1
         for stt in self.states:
             plan = stt.plan
             k, n, off = plan.b_local, plan.n_total, plan.offset
@@ -432,18 +440,29 @@ class _Run:
                 check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(inv), ptr(yinv),
                                             ptr(o_row), ptr(o_col), ptr(dacc), st),
                       "mmcl_sim_grad_bwd")
-                if key not in grads32:
-                    grads32[key] = torch.zeros(src.shape, dtype=torch.float32, device=dev)
                 s_c = src.detach().contiguous()
+                is_direct = (idx is None and n_terms.get(key, 0) == 1 and k == src.shape[0]
+                             and key not in grads32)
+                if is_direct:
+                    out_t = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                    direct[key] = out_t
+                    gbuf, gdt = out_t, _DTYPES[src.dtype]
+                else:
+                    if key not in grads32:
+                        grads32[key] = torch.zeros(src.shape, dtype=torch.float32, device=dev)
+                    gbuf, gdt = grads32[key], 0
                 check(lib.mmcl_unpack_grad(h, ptr(dacc), ptr(partner), ptr(pinv), k, d, plan.weight,
                                            pc, ptr(gout), sp, ptr(s_c), _DTYPES[s_c.dtype], ptr(inv),
-                                           int(m.l2_normalize), ptr(idx), ptr(grads32[key]), st),
+                                           int(m.l2_normalize), ptr(idx), ptr(gbuf), gdt,
+                                           int(is_direct), st),
                       "mmcl_unpack_grad")
         out = []
         for key in self.keys:
             src = self.embs[key]
             if not src.requires_grad:
                 out.append(None)
+            elif key in direct:
+                out.append(direct[key])
             elif key in grads32:
                 out.append(grads32[key].to(src.dtype))
             else:

@@ -1,0 +1,50 @@
+"""Kernel timeline of a few fused-loss steps (torch.profiler / CUPTI): per-kernel start, duration
+and the idle gap before it.  usage: python tools/step_timeline.py [N] [d] [steps]"""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+d = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(1234)
+a = torch.randn(N, d, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+b = (0.5 * a.detach().float().cpu() + torch.randn(N, d, generator=g)).to(torch.bfloat16).to(dev).requires_grad_(True)
+ids = torch.stack([torch.zeros(N, dtype=torch.long), torch.arange(N)], 1).to(dev)
+log_s = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True, cache_labels=True)
+pairs = [LossPairSpec(("rgb", "text"))]
+
+
+def step():
+    a.grad = b.grad = log_s.grad = None
+    loss = fn({"rgb_embedding": a, "text_embedding": b}, {"rgb": ids, "text": ids}, log_s.exp(), pairs)
+    loss.backward()
+    return loss
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(steps):
+        step()
+        torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+t0 = evs[0].time_range.start
+prev_end = t0
+tot_busy = 0.0
+for e in evs:
+    st, en = e.time_range.start, e.time_range.end
+    print(f"{(st - t0):10.1f} us  dur {(en - st):9.1f}  gap {(st - prev_end):8.1f}  {e.name[:70]}")
+    prev_end = max(prev_end, en)
+    tot_busy += en - st
+print(f"span {(prev_end - t0):.1f} us, busy {tot_busy:.1f} us over {steps} steps")
