@@ -205,7 +205,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t) / args.steps
     value = N / (ms_per_step * 1e-3)
-    loss_value = float(loss)
+    loss_value = float(loss.detach())
 
     # ---- (2) end to end: pinned host buffers -> H2D -> step -> D2H of loss + d(scale) -----------
     e2e_steps = args.steps
@@ -267,8 +267,13 @@ def main():
         flops = 4.0 * b * N * d  # two of the reference's four backward GEMMs per launch
         achieved = flops / (kms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops"])
-        roof = {"bound": "tensor", "kernel": "sim_grad_bwd_kernel", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
+        # `ncu --set full` capture at this shape (profiles/r01_ncu_summary.md); algorithmic
+        # operand + result bytes are (b + N) * d * 2 + b * d * 4
+        traffic = 220.6e6 if (N, d, world) == (32768, 512, 1) else None
+        roof = {"bound": "tensor", "kernel": "sim_grad_bwd_pair_kernel", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes": (b + N) * d * 2 + b * d * 4,
                 "ms_per_launch": kms, "peak_source": f"{peaks['_source']} burst cuBLAS bf16",
                 "step_tflops": 12.0 * b * N * d / (ms_per_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": 12.0 * b * N * d / (ms_per_step * 1e-3) / 1e12
