@@ -92,6 +92,10 @@ int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_r
  * contrastive.py:431-578 (all-gather, and the reduce-scatter that autograd's all-gather
  * performs in backward, contrastive.py:506).
  * ------------------------------------------------------------------------------------------ */
+/* Bracket several collective calls so that NCCL launches them as one fused operation
+ * (ncclGroupStart / ncclGroupEnd); no-ops for world == 1. */
+int mmcl_group_start(mmcl_handle* h);
+int mmcl_group_end(mmcl_handle* h);
 int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int64_t* counts,
                          int64_t row_bytes, mmcl_stream stream);
 int mmcl_reduce_scatter_rows_f32(mmcl_handle* h, const float* send, float* recv,

@@ -25,6 +25,8 @@ SYMBOLS = {
                                c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmcl_pack_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64,
                                c_int, c_void_p, c_void_p, c_void_p]),
+    "mmcl_group_start": (c_int, [c_void_p]),
+    "mmcl_group_end": (c_int, [c_void_p]),
     "mmcl_all_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64,
                                      c_void_p]),
     "mmcl_reduce_scatter_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64),

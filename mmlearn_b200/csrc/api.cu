@@ -153,6 +153,20 @@ int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_r
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_pack_rows");
 }
 
+int mmcl_group_start(mmcl_handle* h) {
+  REQUIRE(h, "mmcl_group_start: null handle");
+  if (h->world == 1) return MMCL_OK;
+  ncclResult_t r = ncclGroupStart();
+  return r == ncclSuccess ? MMCL_OK : nccl_fail(r, "ncclGroupStart");
+}
+
+int mmcl_group_end(mmcl_handle* h) {
+  REQUIRE(h, "mmcl_group_end: null handle");
+  if (h->world == 1) return MMCL_OK;
+  ncclResult_t r = ncclGroupEnd();
+  return r == ncclSuccess ? MMCL_OK : nccl_fail(r, "ncclGroupEnd");
+}
+
 int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int64_t* counts,
                          int64_t row_bytes, mmcl_stream stream) {
   REQUIRE(h && counts && row_bytes > 0, "mmcl_all_gather_rows: bad arguments");

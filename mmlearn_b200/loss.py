@@ -161,13 +161,10 @@ class _Run:
 
     # ------------------------------------------------------------------------------------
     def forward(self, logit_scale: torch.Tensor, embs):
-        lib = _lib.load()
         m = self.m
         world, rank = dist_info()
         dev = embs[0].device
-        h = get_handle(dev)
-        st = _stream(dev)
-        self.dev, self.h = dev, h
+        self.dev, self.h = dev, get_handle(dev)
         self.embs = dict(zip(self.keys, embs))
         self.scale_shape, self.scale_dtype = logit_scale.shape, logit_scale.dtype
         P = len(self.pairs)
@@ -177,7 +174,36 @@ class _Run:
                 f"logit_scale must be a scalar or have one entry per modality pair ({P}), got "
                 f"shape {tuple(logit_scale.shape)}")
         self.scale = scale
-        d = embs[0].shape[-1]
+        # The host needs the per-rank match counts of every pair to size buffers and order the
+        # collectives.  Reading them costs a device->host sync at the very start of the step,
+        # with an idle GPU.  When the previous step with the same signature produced a table,
+        # the step is enqueued against that table and the table is verified with ONE sync after
+        # all forward work has been queued; a mismatch (ids changed structure) re-runs the step.
+        # The cache key holds only what every rank shares (pairs, world, train/eval), so all
+        # ranks always take the same branch and issue the same collectives with the same sizes;
+        # a rank whose local batch no longer fits the table still goes through the motions and
+        # the verification (which sees every rank's fresh table) fails on all ranks together.
+        sig = (world, tuple(tuple(pr.modalities) for pr in self.pairs), bool(self.need_grad))
+        assumed = m._plan_cache.get(sig) if m.speculate else None
+        if assumed is not None:
+            res = self._forward_impl(assumed)
+            if res is not None:
+                return res
+            self.states = []  # mis-speculation: fall through to the synchronous path
+            m._plan_cache.pop(sig, None)
+        res = self._forward_impl(None)
+        m._plan_cache[sig] = self.all_info
+        return res
+
+    def _forward_impl(self, assumed: Optional[torch.Tensor]):
+        lib = _lib.load()
+        m = self.m
+        world, rank = dist_info()
+        dev, h = self.dev, self.h
+        st = _stream(dev)
+        P = len(self.pairs)
+        scale = self.scale
+        d = next(iter(self.embs.values())).shape[-1]
 
         # ---- 1. local id matching (contrastive.py:268-291), all pairs in flight at once ----
         ids = {}
@@ -190,22 +216,30 @@ class _Run:
 
         matches: list[Optional[_Match]] = []
         mods = []
-        for pair in self.pairs:
+        sizes = torch.zeros(P, 2, dtype=torch.long)
+        for p, pair in enumerate(self.pairs):
             ma = Modalities.get_modality(pair.modalities[0])
             mb = Modalities.get_modality(pair.modalities[1])
             mods.append((ma, mb))
             if ma.embedding in self.embs and mb.embedding in self.embs:
                 _validate_ids(self.example_ids[ma.name], self.example_ids[mb.name])
                 matches.append(_Match(h, ids_of(ma.name), ids_of(mb.name)))
+                sizes[p, 0], sizes[p, 1] = ids_of(ma.name).shape[0], ids_of(mb.name).shape[0]
             else:
                 matches.append(None)
-        info = torch.zeros(P, 2, dtype=torch.long, device=dev)
+        # per pair: [k, identity, rows of ids_a, rows of ids_b]
+        info = torch.zeros(P, 4, dtype=torch.long, device=dev)
+        info[:, 2:] = sizes.to(dev, non_blocking=True)
         for p, mt in enumerate(matches):
             if mt is not None:
-                info[p] = mt.info
-        # one exchange: [k, identity] per pair from every rank (replaces contrastive.py:197-206
-        # and the shape gathers of _gather_all_tensors)
-        all_info = all_gather_ints(info.view(-1), world).view(world, P, 2).cpu()  # host sync
+                info[p, :2] = mt.info
+        # one exchange: the table of every rank (replaces contrastive.py:197-206 and the shape
+        # gathers of _gather_all_tensors)
+        all_info_dev = all_gather_ints(info.view(-1), world).view(world, P, 4)
+        all_info = all_info_dev.cpu() if assumed is None else assumed  # host sync (first step)
+        self.all_info = all_info
+        verify: list = []  # (device scalar, expected int) pairs checked at the end (speculation)
+        gcache: dict = {}
 
         # ---- 2. per pair: pack matched rows straight into the gather buffer, all-gather ----
         out2 = torch.zeros(P, 2, dtype=torch.float32, device=dev)
@@ -225,14 +259,20 @@ class _Run:
             stt.scale_index = p if scale.numel() > 1 else 0
             k = plan.b_local
             ident = bool(all_info[rank, p, 1]) and k > 0
-            if k > 0:
-                ia, ib = matches[p].finish(k)
-                stt.idx_a, stt.idx_b = (None, None) if ident else (ia, ib)
-            else:
-                stt.idx_a = stt.idx_b = None
+            stt.idx_a = stt.idx_b = None
+            if k > 0 and not ident:
+                if matches[p] is not None and (assumed is None or k <= matches[p].capacity):
+                    stt.idx_a, stt.idx_b = matches[p].finish(k)
+                # else: the assumed table does not fit this rank's batch; the step is queued
+                # anyway (same collectives as every other rank) and fails verification
             all_ident = all(bool(all_info[r, p, 1]) or counts[r] == 0 for r in range(world))
             if world > 1:
-                self._check_global_order(ma, mb, ids_of, counts, world)
+                kg = self._global_match_count(ma, mb, ids_of, all_info[:, p, 2].tolist(),
+                                              all_info[:, p, 3].tolist(), gcache)
+                if assumed is None:
+                    self._raise_if_cross_rank(ma, mb, int(kg.item()), n_total)
+                else:
+                    verify.append((kg, n_total))
 
             def gathered(key, idx, name):
                 """Raw bf16 rows of every rank's matched samples, [N, d], plus their fp32
@@ -245,7 +285,7 @@ class _Run:
                 f_all = torch.empty(n_total, d, dtype=torch.bfloat16, device=dev)
                 inv_all = (torch.empty(n_total, dtype=torch.float32, device=dev)
                            if m.l2_normalize else None)
-                if k > 0:
+                if k > 0 and src is not None and src.shape[0] > 0:
                     s_c = src.detach().contiguous()
                     if s_c.dtype not in _DTYPES:
                         raise ValueError(f"unsupported embedding dtype {s_c.dtype}")
@@ -266,8 +306,12 @@ class _Run:
                     shared[ck] = (f_all, inv_all)
                 return f_all, inv_all
 
+            if world > 1:
+                check(lib.mmcl_group_start(h), "mmcl_group_start")
             stt.fa_all, stt.inv_a = gathered(ma.embedding, stt.idx_a, ma.name)
             stt.fb_all, stt.inv_b = gathered(mb.embedding, stt.idx_b, mb.name)
+            if world > 1:
+                check(lib.mmcl_group_end(h), "mmcl_group_end")
             self.states.append(stt)
             if m.cache_labels:
                 m._remember_labels(plan, dev)
@@ -280,11 +324,8 @@ class _Run:
             fa = stt.fa_all[off:off + k]
             fb = stt.fb_all[off:off + k]
             sp = scale.data_ptr() + 4 * stt.scale_index
-            lse_a = torch.empty(k, dtype=torch.float32, device=dev)
-            lse_b = torch.empty(k, dtype=torch.float32, device=dev)
-            es_a = torch.empty(k, dtype=torch.float32, device=dev)
-            es_b = torch.empty(k, dtype=torch.float32, device=dev)
-            pos = torch.empty(k, dtype=torch.float32, device=dev)
+            vec = torch.empty(5, k, dtype=torch.float32, device=dev)
+            lse_a, lse_b, es_a, es_b, pos = vec[0], vec[1], vec[2], vec[3], vec[4]
             ws_bytes = lib.mmcl_sim_lse_workspace_bytes(h, k, n_total, d)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             ia_loc = stt.inv_a[off:off + k] if stt.inv_a is not None else None
@@ -313,6 +354,7 @@ class _Run:
         # forward, so that backward issues no collective at all (a rank whose loss is a constant
         # 0 never runs backward; the reference deadlocks in that situation).
         if need_grad and world > 1:
+            check(lib.mmcl_group_start(h), "mmcl_group_start")
             for stt in self.states:
                 plan = stt.plan
                 if plan.col_denominators() is None:
@@ -326,47 +368,61 @@ class _Run:
                                                    counts_array(plan.counts), 4, st),
                           "mmcl_all_gather_rows")
                     setattr(stt, name + "_all", full)
+            check(lib.mmcl_group_end(h), "mmcl_group_end")
         self.losses_present = losses_present
         loss = out2[:, 0].sum()
         dscale = out2[:, 1].clone() if scale.numel() > 1 else out2[:, 1].sum()
+
+        if assumed is not None:
+            # ---- verification of the assumed table: the step's only host sync ----
+            got = torch.cat([all_info_dev.reshape(-1)] + [kg.reshape(1) for kg, _ in verify]).cpu()
+            want = torch.cat([assumed.reshape(-1),
+                              torch.tensor([e for _, e in verify], dtype=torch.long)])
+            if not torch.equal(got, want):
+                return None
         return loss, dscale
 
     # ------------------------------------------------------------------------------------
-    def _check_global_order(self, ma, mb, ids_of, counts, world):
-        """The reference matches the *gathered* ids again (contrastive.py:310-313).  The fused
-        path needs the result only to confirm that the global match list is the concatenation of
-        the local ones (true unless an example id occurs on two ranks)."""
+    def _global_match_count(self, ma, mb, ids_of, sizes_a, sizes_b, cache) -> torch.Tensor:
+        """Number of matches between the gathered id lists (device scalar, no host sync).
+        The reference matches the *gathered* ids again (contrastive.py:310-313); the fused path
+        needs the result only to confirm that the global match list is the concatenation of the
+        local ones (true unless an example id occurs on two ranks)."""
         lib = _lib.load()
         key = ("gcheck", ma.name, mb.name)
-        cache = self.__dict__.setdefault("_gcheck", {})
         if key in cache:
-            return
+            return cache[key]
         dev, h, st = self.dev, self.h, _stream(self.dev)
+        rank = dist.get_rank()
 
-        def gather_ids(name):
+        def gather_ids(name, sizes):
             ck = ("ids", name)
             if ck in cache:
                 return cache[ck]
+            sizes = [int(x) for x in sizes]
             loc = ids_of(name) if name in self.example_ids else torch.empty(0, 2, dtype=torch.long,
                                                                             device=dev)
-            sizes = all_gather_ints(torch.tensor([loc.shape[0]], device=dev), world).view(-1).cpu()
-            sizes = [int(x) for x in sizes]
             full = torch.empty(sum(sizes), 2, dtype=torch.long, device=dev)
-            off = sum(sizes[: dist.get_rank()])
-            if loc.shape[0]:
-                full[off:off + loc.shape[0]].copy_(loc)
+            off = sum(sizes[:rank])
+            nloc = min(loc.shape[0], sizes[rank])  # differs only under a stale assumed table
+            if nloc:
+                full[off:off + nloc].copy_(loc[:nloc])
             check(lib.mmcl_all_gather_rows(h, full.data_ptr() + off * 16, ptr(full),
                                            counts_array(sizes), 16, st), "mmcl_all_gather_rows")
             cache[ck] = full
             return full
 
-        ga, gb = gather_ids(ma.name), gather_ids(mb.name)
+        ga, gb = gather_ids(ma.name, sizes_a), gather_ids(mb.name, sizes_b)
         mt = _Match(h, ga, gb, capacity=1)
-        k_global = int(mt.info[0].item())
-        cache[key] = k_global
-        if k_global != sum(counts):
+        cache[key] = mt.info[0]
+        cache[("keep", key)] = mt  # buffers stay alive until the kernels have run
+        return cache[key]
+
+    @staticmethod
+    def _raise_if_cross_rank(ma, mb, k_global: int, n_total: int) -> None:
+        if k_global != n_total:
             raise NotImplementedError(
-                f"pair ({ma.name}, {mb.name}): {k_global} matches across ranks but {sum(counts)} "
+                f"pair ({ma.name}, {mb.name}): {k_global} matches across ranks but {n_total} "
                 "within ranks -- some example id occurs on more than one rank. The reference's "
                 "labels are mis-aligned in that case (SURVEY.md Appendix B); the fused path "
                 "refuses it instead of silently computing something else.")
@@ -507,6 +563,10 @@ class ContrastiveLoss(nn.Module):
         # cache state (same attributes as contrastive.py:55-57; not part of state_dict)
         self._prev_num_logits = 0
         self._labels: dict = {}
+        # match-count table of the previous step per call signature (see _Run.forward); plain
+        # attributes, not buffers: nothing is added to state_dict
+        self._plan_cache: dict = {}
+        self.speculate = True
 
     def _remember_labels(self, plan: PairPlan, device) -> None:
         """contrastive.py:190-219: rebuild when the logit width changes or the device is new."""

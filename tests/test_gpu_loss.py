@@ -114,3 +114,46 @@ def test_eval_no_grad_and_no_pairs():
     z = fn(e, i2, torch.tensor(10.0, device=DEV), [LossPairSpec(("rgb", "text"))])
     assert float(z) == 0.0 and z.dtype == e["rgb_embedding"].dtype
     assert len(fn.state_dict()) == 0
+
+
+def test_cached_plan_speculation():
+    """Second and later calls of one module enqueue the step against the previous step's match
+    table and verify it afterwards; a step whose ids have a different structure must be detected
+    and re-run, and every call must give the reference's numbers."""
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    n, d = 512, 128
+    emb, ids = synthetic_inputs(n, d)
+    flags = dict(l2_normalize=True, local_loss=True, gather_with_grad=True, cache_labels=True)
+    fn = ContrastiveLoss(**flags)
+    pairs = [LossPairSpec(("rgb", "text"))]
+
+    def run(ids_np, emb_t):
+        leaves = {k: v.to(DEV).clone().requires_grad_(True) for k, v in emb_t.items()}
+        s = torch.tensor(1 / 0.07, device=DEV, requires_grad=True)
+        loss = fn(leaves, {k: torch.from_numpy(v).to(DEV) for k, v in ids_np.items()}, s, pairs)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss, leaves, s
+
+    def check(ids_np, emb_t):
+        ref = contrastive_oracle([emb_t], [ids_np], 1 / 0.07, [OPair(("rgb", "text"))],
+                                 l2_normalize=True, local_loss=True, gather_with_grad=True)
+        loss, leaves, s = run(ids_np, emb_t)
+        _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
+
+    check(ids[0], emb[0])            # synchronous first step, fills the cache
+    assert len(fn._plan_cache) == 1
+    check(ids[0], emb[0])            # speculative, verified
+    # same shapes, different structure: text ids permuted and partly unmatched
+    rng = np.random.RandomState(3)
+    ids2 = {k: v.copy() for k, v in ids[0].items()}
+    ids2["text"] = ids2["text"][rng.permutation(n)]
+    ids2["text"][:50, 1] += 100_000
+    check(ids2, emb[0])              # mis-speculation -> re-run
+    check(ids2, emb[0])              # speculative on the new table
+    # different batch size
+    emb3 = {k: v[:300] for k, v in emb[0].items()}
+    ids3 = {k: v[:300] for k, v in ids[0].items()}
+    check(ids3, emb3)
+    check(ids[0], emb[0])

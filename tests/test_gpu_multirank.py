@@ -68,3 +68,62 @@ def test_golden_two_ranks(name):
         assert got["dscale"] == pytest.approx(float(ref["dscale"]), rel=5e-2, abs=2e-3)
         if "labels" in ref and "labels" in got:
             assert np.array_equal(got["labels"], ref["labels"])
+
+
+def _worker_sequence(rank, world, names, init_file, ret):
+    """One module instance fed a sequence of golden cases: exercises the cached-plan
+    speculation (hit, miss with a different table, uneven ranks) under NCCL."""
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world,
+                            device_id=dev)
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    flags = load_case(names[0])["flags"]
+    fn = ContrastiveLoss(modality_alignment=False, **flags)
+    outs = []
+    for name in names:
+        case = load_case(name)
+        assert {k: v for k, v in case["flags"].items() if k != "cache_labels"} == \
+            {k: v for k, v in flags.items() if k != "cache_labels"}
+        leaves = {f"{m}_embedding": torch.from_numpy(v).to(dev).requires_grad_(True)
+                  for m, v in case["emb"][rank].items()}
+        ids = {m: torch.from_numpy(v).to(dev) for m, v in case["ids"][rank].items()}
+        s = torch.tensor(case["scale"], device=dev, dtype=torch.float32, requires_grad=True)
+        loss = fn(leaves, ids, s, [LossPairSpec((a, b), w) for a, b, w in case["pairs"]])
+        if loss.requires_grad:
+            loss.backward()
+        torch.cuda.synchronize()
+        out = {"loss": float(loss.detach())}
+        for k, v in leaves.items():
+            out[f"grad_{k}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).float().cpu().numpy()
+        outs.append(out)
+    ret[rank] = outs
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_speculation_sequence_two_ranks():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    # both cases were generated with l2_normalize, local_loss, gather_with_grad
+    names = ["w2_ll1_gg1", "w2_ll1_gg1", "w2_uneven", "w2_uneven", "w2_ll1_gg1"]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_sequence, args=(2, names, os.path.join(td, "init"), ret), nprocs=2,
+                 join=True)
+    for r in range(2):
+        for name, got in zip(names, ret[r]):
+            ref = load_case(name)["out"][r]
+            assert got["loss"] == pytest.approx(float(ref["loss"]), rel=1e-3, abs=1e-6), name
+            for k in [k for k in got if k.startswith("grad_")]:
+                g, e = torch.from_numpy(got[k]), torch.from_numpy(ref[k])
+                if float(e.norm()) == 0:
+                    assert float(g.norm()) == 0
+                    continue
+                assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2), (name, k)

@@ -13,11 +13,20 @@ from mmlearn_b200 import ContrastiveLoss, LossPairSpec
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-dev = torch.device("cuda:0")
-g = torch.Generator().manual_seed(1234)
-a = torch.randn(N, d, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
-b = (0.5 * a.detach().float().cpu() + torch.randn(N, d, generator=g)).to(torch.bfloat16).to(dev).requires_grad_(True)
-ids = torch.stack([torch.zeros(N, dtype=torch.long), torch.arange(N)], 1).to(dev)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", device_id=dev)
+nb = N // world  # rows of this rank (global batch N)
+g = torch.Generator().manual_seed(1234 + rank)
+a = torch.randn(nb, d, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+b = (0.5 * a.detach().float().cpu() + torch.randn(nb, d, generator=g)).to(torch.bfloat16).to(dev).requires_grad_(True)
+ids = torch.stack([torch.zeros(nb, dtype=torch.long), torch.arange(rank * nb, (rank + 1) * nb)], 1).to(dev)
 log_s = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
 fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True, cache_labels=True)
 pairs = [LossPairSpec(("rgb", "text"))]
@@ -37,6 +46,11 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(steps):
         step()
         torch.cuda.synchronize()
+if rank != 0:
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 t0 = evs[0].time_range.start
@@ -48,3 +62,6 @@ for e in evs:
     prev_end = max(prev_end, en)
     tot_busy += en - st
 print(f"span {(prev_end - t0):.1f} us, busy {tot_busy:.1f} us over {steps} steps")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
