@@ -62,8 +62,8 @@ int mmcl_destroy(mmcl_handle* h);
  * contrastive.py:279-282 and :310-313).  ids_* are int64 [n,2] / [m,2] row-major on the device.
  * Output order is torch.where's: ascending index into a, then ascending index into b;
  * duplicate ids yield the cross product (reference test tests/datasets/test_example.py:159-168).
- * At most `capacity` pairs are written to out_a/out_b; out_info (device int64[2]) receives
- * {k = total number of matches, identity = 1 iff n == m and the result is (arange, arange)}.
+ * At most `capacity` pairs are written to out_a/out_b; out_info (device int64[4]) receives
+ * {k = total number of matches, identity = 1 iff n == m and the result is (arange, arange), n, m}.
  * The caller reads out_info (its only host sync) and retries with capacity >= k if needed.
  * ------------------------------------------------------------------------------------------ */
 size_t mmcl_match_workspace_bytes(int64_t n, int64_t m);
@@ -71,6 +71,14 @@ int mmcl_match_ids(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_
                    int64_t m, int64_t* out_a, int64_t* out_b, int64_t capacity,
                    int64_t* out_info, void* workspace, size_t workspace_bytes,
                    mmcl_stream stream);
+
+/* Cheap test of the common case "the match is the identity": out_info (device int64[4]) =
+ * {n, 1, n, m} iff n == m, ids_a[j] == ids_b[j] for all j and all ids are distinct, otherwise
+ * {0, 0, n, m} (the caller then runs mmcl_match_ids).  One hash-insert pass, no scans. */
+size_t mmcl_identity_check_workspace_bytes(int64_t m);
+int mmcl_identity_check(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_t* ids_b,
+                        int64_t m, int64_t* out_info, void* workspace, size_t workspace_bytes,
+                        mmcl_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row packing: dst[i,:] = bf16( src[idx[i],:] ), inv_norm[i] = 1/max(|src row|,1e-12)
@@ -149,7 +157,17 @@ int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void
                       const float* yinv, const float* off_row, const float* off_col, float* dx,
                       mmcl_stream stream);
 
-/* off[i] = log2(e) * lse[i] + log2(denom[i] or denom_scalar)  (helper for the call above) */
+/* Same kernel, taking the log-sum-exp vectors themselves: off_row[i] = log2(e)*lse_row[i] +
+ * log2(row_den), off_col[j] = log2(e)*lse_col[j] + log2(col_den) are formed on the fly (one
+ * denominator per vector; per-row denominators need mmcl_make_offsets + mmcl_sim_grad_bwd).
+ * zero_dx != 0 clears dx on the stream first. */
+int mmcl_sim_grad_bwd_lse(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16,
+                          int64_t ny, int64_t d, const float* scale, const float* xinv,
+                          const float* yinv, const float* lse_row, double row_den,
+                          const float* lse_col, double col_den, float* dx, int zero_dx,
+                          mmcl_stream stream);
+
+/* off[i] = log2(e) * lse[i] + log2(denom[i] or denom_scalar)  (helper for mmcl_sim_grad_bwd) */
 int mmcl_make_offsets(mmcl_handle* h, const float* lse, int64_t n, const float* denom_vec,
                       double denom_scalar, float* off, mmcl_stream stream);
 

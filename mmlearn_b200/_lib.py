@@ -23,6 +23,9 @@ SYMBOLS = {
     "mmcl_match_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "mmcl_match_ids": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmcl_identity_check_workspace_bytes": (c_size_t, [c_int64]),
+    "mmcl_identity_check": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
     "mmcl_pack_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64,
                                c_int, c_void_p, c_void_p, c_void_p]),
     "mmcl_group_start": (c_int, [c_void_p]),
@@ -43,6 +46,9 @@ SYMBOLS = {
     "mmcl_sim_grad_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "mmcl_sim_grad_bwd_lse": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
+                                      c_double, c_void_p, c_int, c_void_p]),
     "mmcl_make_offsets": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_double, c_void_p,
                                   c_void_p]),
     "mmcl_unpack_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,

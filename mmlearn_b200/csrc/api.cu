@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -136,6 +137,25 @@ int mmcl_match_ids(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_
   cudaError_t e = launch_match_ids(ids_a, n, ids_b, m, out_a, out_b, capacity, out_info, workspace,
                                    workspace_bytes, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_match_ids");
+}
+
+size_t mmcl_identity_check_workspace_bytes(int64_t m) {
+  return identity_check_workspace_bytes(m);
+}
+
+int mmcl_identity_check(mmcl_handle* h, const int64_t* ids_a, int64_t n, const int64_t* ids_b,
+                        int64_t m, int64_t* out_info, void* workspace, size_t workspace_bytes,
+                        mmcl_stream stream) {
+  REQUIRE(h && out_info, "mmcl_identity_check: null handle/out_info");
+  REQUIRE(n >= 0 && m >= 0 && n < (1ll << 31) && m < (1ll << 31), "mmcl_identity_check: bad size");
+  REQUIRE((n == 0 || ids_a) && (m == 0 || ids_b), "mmcl_identity_check: null ids");
+  if (n == m && n > 0 && (workspace_bytes < identity_check_workspace_bytes(m) || !workspace))
+    return fail(MMCL_ERR_WORKSPACE, "mmcl_identity_check: workspace too small");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_identity_check(ids_a, n, ids_b, m, out_info, workspace, workspace_bytes,
+                                        static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_identity_check");
 }
 
 int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_rows, int64_t d,
@@ -342,9 +362,39 @@ int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void
   DeviceGuard g(h->device);
   const char* err = nullptr;
   cudaError_t e = launch_sim_grad_bwd(h->num_sms, x_bf16, nx, y_bf16, ny, d, scale, xinv, yinv,
-                                      off_row, off_col, dx, static_cast<cudaStream_t>(stream),
-                                      &err);
+                                      off_row, off_col, 1.f, 0.f, 0.f, dx,
+                                      static_cast<cudaStream_t>(stream), &err);
   if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_grad_bwd");
+  return MMCL_OK;
+}
+
+int mmcl_sim_grad_bwd_lse(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16,
+                          int64_t ny, int64_t d, const float* scale, const float* xinv,
+                          const float* yinv, const float* lse_row, double row_den,
+                          const float* lse_col, double col_den, float* dx, int zero_dx,
+                          mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_sim_grad_bwd_lse: null handle/scale");
+  int rc = check_sim_args("mmcl_sim_grad_bwd_lse", x_bf16, nx, y_bf16, ny, d);
+  if (rc) return rc;
+  if (nx == 0) return MMCL_OK;
+  REQUIRE(dx, "mmcl_sim_grad_bwd_lse: null dx");
+  REQUIRE((!lse_row || row_den > 0) && (!lse_col || col_den > 0),
+          "mmcl_sim_grad_bwd_lse: denominators must be positive");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (zero_dx) {
+    cudaError_t e = cudaMemsetAsync(dx, 0, size_t(nx) * size_t(d) * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "mmcl_sim_grad_bwd_lse (memset)");
+  }
+  if (ny == 0) return MMCL_OK;
+  const char* err = nullptr;
+  const float log2e = 1.4426950408889634f;
+  cudaError_t e = launch_sim_grad_bwd(
+      h->num_sms, x_bf16, nx, y_bf16, ny, d, scale, xinv, yinv, lse_row, lse_col, log2e,
+      lse_row ? float(log2(row_den)) : 0.f, lse_col ? float(log2(col_den)) : 0.f, dx, st, &err);
+  if (e != cudaSuccess)
+    return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_grad_bwd_lse");
   return MMCL_OK;
 }
 

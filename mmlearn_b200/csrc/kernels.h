@@ -21,13 +21,15 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
                                 long long ny, long long d, const float* scale, const float* xinv,
                                 const float* yinv, const float* off_row, const float* off_col,
-                                float* dx, cudaStream_t stream, const char** err);
+                                float off_mul, float row_add, float col_add, float* dx,
+                                cudaStream_t stream, const char** err);
 
 // sim_bwd_pair.cu (cudaErrorNotSupported = shape does not fit, nothing launched)
 cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
                                      long long ny, long long d, const float* scale,
                                      const float* xinv, const float* yinv, const float* off_row,
-                                     const float* off_col, float* dx, cudaStream_t stream,
+                                     const float* off_col, float off_mul, float row_add,
+                                     float col_add, float* dx, cudaStream_t stream,
                                      const char** err);
 
 // aux_kernels.cu
@@ -55,5 +57,10 @@ size_t match_workspace_bytes(long long n, long long m);
 cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* ids_b, long long m,
                              int64_t* out_a, int64_t* out_b, long long capacity, int64_t* out_info,
                              void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+size_t identity_check_workspace_bytes(long long m);
+cudaError_t launch_identity_check(const int64_t* ids_a, long long n, const int64_t* ids_b,
+                                  long long m, int64_t* out_info, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace mmcl

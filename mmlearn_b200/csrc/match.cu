@@ -250,9 +250,34 @@ __global__ void emit_kernel(MatchWs w, long long n, long long m, long long* __re
   if (!self) info[1] = 0;  // benign race: every writer stores 0
 }
 
-__global__ void info_init_kernel(long long* info, long long n, long long m) {
-  info[0] = 0;
+__global__ void info_init_kernel(long long* info, long long n, long long m, int quick) {
+  info[0] = (quick && n == m) ? n : 0;
   info[1] = (n == m) ? 1 : 0;
+  info[2] = n;
+  info[3] = m;
+}
+
+// Identity check: ids_a[j] == ids_b[j] for every j and all ids_b distinct (hash insert with
+// duplicate detection).  On any violation info = {0, 0, n, m}.
+__global__ void identity_check_kernel(int* __restrict__ owner, long long T,
+                                      const long long* __restrict__ ids_a,
+                                      const long long* __restrict__ ids_b, long long n,
+                                      long long* __restrict__ info) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long long k0 = ids_b[2 * j], k1 = ids_b[2 * j + 1];
+  bool ok = ids_a[2 * j] == k0 && ids_a[2 * j + 1] == k1;
+  long long h = (long long)(mix(k0, k1) & (unsigned long long)(T - 1));
+  while (ok) {
+    const int o = atomicCAS(&owner[h], -1, (int)j);
+    if (o == -1) break;  // inserted
+    if (ids_b[2 * (long long)o] == k0 && ids_b[2 * (long long)o + 1] == k1) ok = false;  // duplicate
+    h = (h + 1) & (T - 1);
+  }
+  if (!ok) {  // benign race: every writer stores the same values
+    info[0] = 0;
+    info[1] = 0;
+  }
 }
 
 }  // namespace
@@ -266,7 +291,7 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
                              int64_t* out_a, int64_t* out_b, long long capacity, int64_t* out_info,
                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   auto* info = reinterpret_cast<long long*>(out_info);
-  info_init_kernel<<<1, 1, 0, stream>>>(info, n, m);
+  info_init_kernel<<<1, 1, 0, stream>>>(info, n, m, 0);
   count_launches(1);
   if (n == 0 || m == 0) return cudaGetLastError();
   MatchWs w;
@@ -285,6 +310,26 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
   emit_kernel<<<blocks(n), B, 0, stream>>>(w, n, m, reinterpret_cast<long long*>(out_a),
                                            reinterpret_cast<long long*>(out_b), capacity, info);
   count_launches(12);
+  return cudaGetLastError();
+}
+
+size_t identity_check_workspace_bytes(long long m) { return size_t(table_size(m > 0 ? m : 1)) * 4; }
+
+cudaError_t launch_identity_check(const int64_t* ids_a, long long n, const int64_t* ids_b,
+                                  long long m, int64_t* out_info, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+  auto* info = reinterpret_cast<long long*>(out_info);
+  info_init_kernel<<<1, 1, 0, stream>>>(info, n, m, 1);
+  count_launches(1);
+  if (n != m || n == 0) return cudaGetLastError();
+  const long long T = table_size(m);
+  if (size_t(T) * 4 > workspace_bytes) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(workspace, 0xFF, size_t(T) * 4, stream);  // owner = -1
+  if (e != cudaSuccess) return e;
+  identity_check_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+      static_cast<int*>(workspace), T, reinterpret_cast<const long long*>(ids_a),
+      reinterpret_cast<const long long*>(ids_b), n, info);
+  count_launches(1);
   return cudaGetLastError();
 }
 

@@ -42,6 +42,7 @@ struct BwdParams {
   const float* yinv;  // [ny] 1/||y_j|| or null
   const float* off_row;
   const float* off_col;
+  float off_mul, row_add, col_add;  // offset = off_*[i] * off_mul + *_add (lets callers pass raw lse)
   float* dx;
 };
 
@@ -130,12 +131,12 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // range of all offsets: decides whether the one-exponential form of G is safe
     float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < p.nx; i += 256) {
-      const float v = p.off_row[i];
+      const float v = fmaf(p.off_row[i], p.off_mul, p.row_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
     for (int i = threadIdx.x; i < p.ny; i += 256) {
-      const float v = p.off_col[i];
+      const float v = fmaf(p.off_col[i], p.off_mul, p.col_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
@@ -294,7 +295,7 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       if (yt1 > p.nyt) yt1 = p.nyt;
       const int xt = int(item / p.ndc), dc = int(item % p.ndc);
       const int grow = xt * BM + row;
-      const float offr = (p.off_row && grow < p.nx) ? p.off_row[grow] : INFINITY;
+      const float offr = (p.off_row && grow < p.nx) ? fmaf(p.off_row[grow], p.off_mul, p.row_add) : INFINITY;
       const float c = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
       const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
       for (int yt = yt0; yt < yt1; ++yt) {
@@ -302,7 +303,7 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int j = et; j < BNY; j += 128) {
           const int gy = yt * BNY + j;
           float2 v2;
-          v2.x = (p.off_col && gy < p.ny) ? p.off_col[gy] : INFINITY;
+          v2.x = (p.off_col && gy < p.ny) ? fmaf(p.off_col[gy], p.off_mul, p.col_add) : INFINITY;
           v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
           if (fast) v2.x = ex2f(mu - v2.x) * v2.y;
           sCol[j] = v2;
@@ -366,7 +367,8 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
                                 long long ny, long long d, const float* scale, const float* xinv,
                                 const float* yinv, const float* off_row, const float* off_col,
-                                float* dx, cudaStream_t stream, const char** err) {
+                                float off_mul, float row_add, float col_add, float* dx,
+                                cudaStream_t stream, const char** err) {
   if (!off_row && !off_col) return cudaSuccess;  // G == 0
   // CTA-pair form first (every logit tile computed once); MMCL_BWD_SINGLE=1 forces this file's
   // single-CTA kernel (used by the tests to cover both).
@@ -376,7 +378,7 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
   }();
   if (!force_single) {
     cudaError_t pe = launch_sim_grad_bwd_pair(num_sms, x, nx, y, ny, d, scale, xinv, yinv, off_row,
-                                              off_col, dx, stream, err);
+                                              off_col, off_mul, row_add, col_add, dx, stream, err);
     if (pe != cudaErrorNotSupported) return pe;
   }
   BwdParams p;
@@ -396,6 +398,9 @@ cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const 
   p.yinv = yinv;
   p.off_row = off_row;
   p.off_col = off_col;
+  p.off_mul = off_mul;
+  p.row_add = row_add;
+  p.col_add = col_add;
   p.dx = dx;
   const size_t budget = 227 * 1024 - 2 * BNY * sizeof(float) - 512;
   const bool xres = size_t(p.kchunks) * XCHUNK_BYTES + 3 * size_t(YBOX_BYTES) <= budget;

@@ -79,6 +79,7 @@ struct PairParams {
   const float* yinv;
   const float* off_row;
   const float* off_col;
+  float off_mul, row_add, col_add;  // offset = off_*[i] * off_mul + *_add (lets callers pass raw lse)
   float* dx;
 };
 
@@ -165,12 +166,12 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     // range of all offsets: decides whether the one-exponential form of G is safe
     float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < p.nx; i += NTHREADS) {
-      const float v = p.off_row[i];
+      const float v = fmaf(p.off_row[i], p.off_mul, p.row_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
     for (int i = threadIdx.x; i < p.ny; i += NTHREADS) {
-      const float v = p.off_col[i];
+      const float v = fmaf(p.off_col[i], p.off_mul, p.col_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
@@ -380,7 +381,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
       const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
       const int grow = xt * BM + row;
       if (own) {
-        const float offr = (p.off_row && grow < p.nx) ? p.off_row[grow] : INFINITY;
+        const float offr = (p.off_row && grow < p.nx) ? fmaf(p.off_row[grow], p.off_mul, p.row_add) : INFINITY;
         const float cc = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
         const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
         named_bar_sync(1 + 2 * wg, 128);  // the warpgroup is done with the previous column data
@@ -388,7 +389,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           const int j = wg * 128 + et;
           const int gy = yt * BNY + j;
           float2 v2;
-          v2.x = (p.off_col && gy < p.ny) ? p.off_col[gy] : INFINITY;
+          v2.x = (p.off_col && gy < p.ny) ? fmaf(p.off_col[gy], p.off_mul, p.col_add) : INFINITY;
           v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
           if (fast) v2.x = ex2f(mu - v2.x) * v2.y;
           sCol[j] = v2;
@@ -490,7 +491,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
 cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
                                      long long ny, long long d, const float* scale,
                                      const float* xinv, const float* yinv, const float* off_row,
-                                     const float* off_col, float* dx, cudaStream_t stream,
+                                     const float* off_col, float off_mul, float row_add,
+                                     float col_add, float* dx, cudaStream_t stream,
                                      const char** err) {
   if (!off_row && !off_col) return cudaSuccess;  // G == 0
   const int ndc = int((d + 511) / 512);
@@ -515,6 +517,9 @@ cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, c
   p.yinv = yinv;
   p.off_row = off_row;
   p.off_col = off_col;
+  p.off_mul = off_mul;
+  p.row_add = row_add;
+  p.col_add = col_add;
   p.dx = dx;
   const size_t smem =
       size_t(NSTAGES) * STAGE_BYTES + STG_BYTES + BNY * sizeof(float2) + XFER_BYTES + TAIL_BYTES;

@@ -82,17 +82,29 @@ def _validate_ids(first, second) -> None:
 
 
 class _Match:
-    """An in-flight device id match; ``info`` = [k, identity] (device int64)."""
+    """An in-flight device id match; ``info`` = [k, identity, n, m] (device int64).
 
-    def __init__(self, h, ids_a: torch.Tensor, ids_b: torch.Tensor, capacity: Optional[int] = None):
+    ``quick=True`` only tests whether the match is the identity (``mmcl_identity_check``):
+    ``info`` is then [n, 1, n, m] or [0, 0, n, m] and no index lists exist."""
+
+    def __init__(self, h, ids_a: torch.Tensor, ids_b: torch.Tensor, capacity: Optional[int] = None,
+                 info: Optional[torch.Tensor] = None, quick: bool = False):
         lib = _lib.load()
-        self.h, self.ids_a, self.ids_b = h, ids_a, ids_b
+        self.h, self.ids_a, self.ids_b, self.quick = h, ids_a, ids_b, quick
         dev = ids_a.device
         n, m = ids_a.shape[0], ids_b.shape[0]
+        self.info = info if info is not None else torch.empty(4, dtype=torch.long, device=dev)
+        if quick:
+            self.capacity = 0
+            ws_bytes = lib.mmcl_identity_check_workspace_bytes(m)
+            self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            check(lib.mmcl_identity_check(h, ptr(ids_a), n, ptr(ids_b), m, ptr(self.info),
+                                          ptr(self.ws), self.ws.numel(), _stream(dev)),
+                  "mmcl_identity_check")
+            return
         self.capacity = max(n, m, 1) if capacity is None else capacity
         self.out_a = torch.empty(self.capacity, dtype=torch.long, device=dev)
         self.out_b = torch.empty(self.capacity, dtype=torch.long, device=dev)
-        self.info = torch.empty(2, dtype=torch.long, device=dev)
         ws_bytes = lib.mmcl_match_workspace_bytes(n, m)
         self.ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         check(lib.mmcl_match_ids(h, ptr(ids_a), n, ptr(ids_b), m, ptr(self.out_a), ptr(self.out_b),
@@ -216,23 +228,21 @@ class _Run:
 
         matches: list[Optional[_Match]] = []
         mods = []
-        sizes = torch.zeros(P, 2, dtype=torch.long)
+        # per pair: [k, identity, rows of ids_a, rows of ids_b], written by the matcher itself
+        info = torch.zeros(P, 4, dtype=torch.long, device=dev)
         for p, pair in enumerate(self.pairs):
             ma = Modalities.get_modality(pair.modalities[0])
             mb = Modalities.get_modality(pair.modalities[1])
             mods.append((ma, mb))
             if ma.embedding in self.embs and mb.embedding in self.embs:
                 _validate_ids(self.example_ids[ma.name], self.example_ids[mb.name])
-                matches.append(_Match(h, ids_of(ma.name), ids_of(mb.name)))
-                sizes[p, 0], sizes[p, 1] = ids_of(ma.name).shape[0], ids_of(mb.name).shape[0]
+                # under an assumed table that says "identity here", only that is tested
+                quick = (assumed is not None and bool(assumed[rank, p, 1])
+                         and int(assumed[rank, p, 0]) > 0)
+                matches.append(_Match(h, ids_of(ma.name), ids_of(mb.name), info=info[p],
+                                      quick=quick))
             else:
                 matches.append(None)
-        # per pair: [k, identity, rows of ids_a, rows of ids_b]
-        info = torch.zeros(P, 4, dtype=torch.long, device=dev)
-        info[:, 2:] = sizes.to(dev, non_blocking=True)
-        for p, mt in enumerate(matches):
-            if mt is not None:
-                info[p, :2] = mt.info
         # one exchange: the table of every rank (replaces contrastive.py:197-206 and the shape
         # gathers of _gather_all_tensors)
         all_info_dev = all_gather_ints(info.view(-1), world).view(world, P, 4)
@@ -261,14 +271,19 @@ class _Run:
             ident = bool(all_info[rank, p, 1]) and k > 0
             stt.idx_a = stt.idx_b = None
             if k > 0 and not ident:
-                if matches[p] is not None and (assumed is None or k <= matches[p].capacity):
+                if matches[p] is not None and not matches[p].quick and (
+                        assumed is None or k <= matches[p].capacity):
                     stt.idx_a, stt.idx_b = matches[p].finish(k)
                 # else: the assumed table does not fit this rank's batch; the step is queued
                 # anyway (same collectives as every other rank) and fails verification
             all_ident = all(bool(all_info[r, p, 1]) or counts[r] == 0 for r in range(world))
             if world > 1:
                 kg = self._global_match_count(ma, mb, ids_of, all_info[:, p, 2].tolist(),
-                                              all_info[:, p, 3].tolist(), gcache)
+                                              all_info[:, p, 3].tolist(), gcache,
+                                              quick=assumed is not None and all(
+                                                  bool(all_info[r, p, 1]) and int(all_info[r, p, 0])
+                                                  == int(all_info[r, p, 2]) == int(all_info[r, p, 3])
+                                                  for r in range(world)))
                 if assumed is None:
                     self._raise_if_cross_rank(ma, mb, int(kg.item()), n_total)
                 else:
@@ -370,8 +385,11 @@ class _Run:
                     setattr(stt, name + "_all", full)
             check(lib.mmcl_group_end(h), "mmcl_group_end")
         self.losses_present = losses_present
-        loss = out2[:, 0].sum()
-        dscale = out2[:, 1].clone() if scale.numel() > 1 else out2[:, 1].sum()
+        if P == 1:
+            loss, dscale = out2[0, 0], (out2[0, 1:2] if scale.numel() > 1 else out2[0, 1])
+        else:
+            loss = out2[:, 0].sum()
+            dscale = out2[:, 1].clone() if scale.numel() > 1 else out2[:, 1].sum()
 
         if assumed is not None:
             # ---- verification of the assumed table: the step's only host sync ----
@@ -383,7 +401,8 @@ class _Run:
         return loss, dscale
 
     # ------------------------------------------------------------------------------------
-    def _global_match_count(self, ma, mb, ids_of, sizes_a, sizes_b, cache) -> torch.Tensor:
+    def _global_match_count(self, ma, mb, ids_of, sizes_a, sizes_b, cache,
+                            quick: bool = False) -> torch.Tensor:
         """Number of matches between the gathered id lists (device scalar, no host sync).
         The reference matches the *gathered* ids again (contrastive.py:310-313); the fused path
         needs the result only to confirm that the global match list is the concatenation of the
@@ -412,8 +431,14 @@ class _Run:
             cache[ck] = full
             return full
 
-        ga, gb = gather_ids(ma.name, sizes_a), gather_ids(mb.name, sizes_b)
-        mt = _Match(h, ga, gb, capacity=1)
+        if quick:
+            # every rank's local match is the identity (verified through the table), so the
+            # global match is the concatenation iff the gathered ids are all distinct
+            gb = gather_ids(mb.name, sizes_b)
+            mt = _Match(h, gb, gb, quick=True)
+        else:
+            ga, gb = gather_ids(ma.name, sizes_a), gather_ids(mb.name, sizes_b)
+            mt = _Match(h, ga, gb, capacity=1)
         cache[key] = mt.info[0]
         cache[("keep", key)] = mt  # buffers stay alive until the kernels have run
         return cache[key]
@@ -454,48 +479,52 @@ class _Run:
             fb = stt.fb_all[off:off + k]
             cden = plan.col_denominators()
 
-            def offsets(lse_loc, lse_all):
-                o_row = torch.empty(k, dtype=torch.float32, device=dev)
-                check(lib.mmcl_make_offsets(h, ptr(lse_loc), k, None, plan.row_denominator(),
-                                            ptr(o_row), st), "mmcl_make_offsets")
-                return o_row
-
-            def col_offsets(lse_loc, lse_all):
-                if cden is None:
-                    return None
-                src = lse_all if plan.world > 1 else lse_loc
-                o = torch.empty(n, dtype=torch.float32, device=dev)
-                if len(set(cden)) == 1:
-                    check(lib.mmcl_make_offsets(h, ptr(src), n, None, cden[0], ptr(o), st),
-                          "mmcl_make_offsets")
-                else:
-                    den = torch.repeat_interleave(
-                        torch.tensor(cden, dtype=torch.float32, device=dev),
-                        torch.tensor(list(plan.counts), device=dev))
-                    check(lib.mmcl_make_offsets(h, ptr(src), n, ptr(den), 1.0, ptr(o), st),
-                          "mmcl_make_offsets")
-                return o
-
-            row_a = offsets(stt.lse_a, None)
-            row_b = offsets(stt.lse_b, None)
-            col_for_a = col_offsets(stt.lse_b, getattr(stt, "lse_b_all", None))  # columns of S
-            col_for_b = col_offsets(stt.lse_a, getattr(stt, "lse_a_all", None))  # rows of S
             pc = plan.positive_coefficient()
             ia_loc = stt.inv_a[off:off + k] if stt.inv_a is not None else None
             ib_loc = stt.inv_b[off:off + k] if stt.inv_b is not None else None
-            for (key, x, y_all, o_row, o_col, partner, inv, yinv, pinv, idx) in (
-                (stt.key_a, fa, stt.fb_all, row_a, col_for_a, fb, ia_loc, stt.inv_b, ib_loc,
-                 stt.idx_a),
-                (stt.key_b, fb, stt.fa_all, row_b, col_for_b, fa, ib_loc, stt.inv_a, ia_loc,
-                 stt.idx_b),
+            # column-term log-sum-exp vectors: all rows of S (gathered) / all columns of S
+            col_lse_for_a = (getattr(stt, "lse_b_all", None) if plan.world > 1 else stt.lse_b)
+            col_lse_for_b = (getattr(stt, "lse_a_all", None) if plan.world > 1 else stt.lse_a)
+            uniform = cden is None or len(set(cden)) == 1
+            if not uniform:
+                # uneven ranks: the column denominator depends on the owning rank, so the offset
+                # vectors are materialised (mmcl_make_offsets) instead of formed in the kernel
+                den = torch.repeat_interleave(
+                    torch.tensor(cden, dtype=torch.float32, device=dev),
+                    torch.tensor(list(plan.counts), device=dev))
+
+                def make_off(lse, num, dvec, dscalar):
+                    o = torch.empty(num, dtype=torch.float32, device=dev)
+                    check(lib.mmcl_make_offsets(h, ptr(lse), num, ptr(dvec), dscalar, ptr(o), st),
+                          "mmcl_make_offsets")
+                    return o
+
+                row_a = make_off(stt.lse_a, k, None, plan.row_denominator())
+                row_b = make_off(stt.lse_b, k, None, plan.row_denominator())
+                col_for_a = make_off(col_lse_for_a, n, den, 1.0)
+                col_for_b = make_off(col_lse_for_b, n, den, 1.0)
+            for (key, x, y_all, lse_row, lse_col, partner, inv, yinv, pinv, idx, side) in (
+                (stt.key_a, fa, stt.fb_all, stt.lse_a, col_lse_for_a, fb, ia_loc, stt.inv_b, ib_loc,
+                 stt.idx_a, 0),
+                (stt.key_b, fb, stt.fa_all, stt.lse_b, col_lse_for_b, fa, ib_loc, stt.inv_a, ia_loc,
+                 stt.idx_b, 1),
             ):
                 src = self.embs[key]
                 if not src.requires_grad:
                     continue
-                dacc = torch.zeros(k, d, dtype=torch.float32, device=dev)
-                check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(inv), ptr(yinv),
-                                            ptr(o_row), ptr(o_col), ptr(dacc), st),
-                      "mmcl_sim_grad_bwd")
+                dacc = torch.empty(k, d, dtype=torch.float32, device=dev)
+                if uniform:
+                    check(lib.mmcl_sim_grad_bwd_lse(
+                        h, ptr(x), k, ptr(y_all), n, d, sp, ptr(inv), ptr(yinv), ptr(lse_row),
+                        plan.row_denominator(), ptr(lse_col) if cden is not None else None,
+                        cden[0] if cden is not None else 1.0, ptr(dacc), 1, st),
+                        "mmcl_sim_grad_bwd_lse")
+                else:
+                    dacc.zero_()
+                    o_row, o_col = (row_a, col_for_a) if side == 0 else (row_b, col_for_b)
+                    check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(inv),
+                                                ptr(yinv), ptr(o_row), ptr(o_col), ptr(dacc), st),
+                          "mmcl_sim_grad_bwd")
                 s_c = src.detach().contiguous()
                 is_direct = (idx is None and n_terms.get(key, 0) == 1 and k == src.shape[0]
                              and key not in grads32)

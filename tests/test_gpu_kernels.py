@@ -170,7 +170,10 @@ def test_match_ids_bit_exact():
 
     ids = torch.stack([torch.zeros(4096, dtype=torch.long), torch.randperm(4096)], 1).to(dev)
     mt = _Match(get_handle(dev), ids, ids.clone())
-    assert mt.info.tolist() == [4096, 1]
+    assert mt.info.tolist() == [4096, 1, 4096, 4096]
+    assert _Match(get_handle(dev), ids, ids.clone(), quick=True).info.tolist() == [4096, 1, 4096, 4096]
     ids2 = ids.clone()
     ids2[5] = ids2[6]
     assert _Match(get_handle(dev), ids, ids2).info.tolist()[1] == 0
+    assert _Match(get_handle(dev), ids, ids2, quick=True).info.tolist() == [0, 0, 4096, 4096]
+    assert _Match(get_handle(dev), ids2, ids2, quick=True).info.tolist() == [0, 0, 4096, 4096]  # duplicate id

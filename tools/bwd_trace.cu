@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
     cudaMemcpyToSymbol(mmcl::g_trace_n, zero, sizeof(zero));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    cudaError_t e = mmcl::launch_sim_grad_bwd_pair(148, x, nx, y, ny, d, scale, nullptr, nullptr, offr, offc, dx, 0, &err);
+    cudaError_t e = mmcl::launch_sim_grad_bwd_pair(148, x, nx, y, ny, d, scale, nullptr, nullptr, offr, offc, 1.f, 0.f, 0.f, dx, 0, &err);
     cudaEventRecord(e1);
     cudaError_t e2 = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
