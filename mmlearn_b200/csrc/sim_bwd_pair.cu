@@ -83,12 +83,13 @@ struct PairParams {
   float* dx;
 };
 
-// exact form, see sim_bwd.cu
+// 16 logits of one row -> 8 packed bf16x2 values of G.  Exact form (see sim_bwd.cu):
+// cy[e] = (off_col[j], 1/||y_j||).
 template <int MODE>
-__device__ __forceinline__ void g_chunk(const uint32_t (&v)[32], uint32_t (&g)[16], float c,
-                                        float offr, const float2* cy) {
+__device__ __forceinline__ void conv16(const uint32_t (&v)[16], uint32_t* g, float c, float offr,
+                                       const float2* cy) {
 #pragma unroll
-  for (int e = 0; e < 32; e += 2) {
+  for (int e = 0; e < 16; e += 2) {
     const float4 f = *reinterpret_cast<const float4*>(cy + e);  // (offc0, yinv0, offc1, yinv1)
     const float x0 = __uint_as_float(v[e]) * f.y, x1 = __uint_as_float(v[e + 1]) * f.w;
     float g0 = 0.f, g1 = 0.f;
@@ -103,15 +104,22 @@ __device__ __forceinline__ void g_chunk(const uint32_t (&v)[32], uint32_t (&g)[1
     g[e >> 1] = pack_bf16x2(g0 * f.y, g1 * f.w);
   }
 }
-// one-exponential form of MODE 3, see sim_bwd.cu
-__device__ __forceinline__ void g_chunk_fast(const uint32_t (&v)[32], uint32_t (&g)[16], float c,
-                                             float offr, float R, const float2* cy) {
+// One-exponential form of MODE 3 (see sim_bwd.cu) on packed fp32x2 math (sm_100 FFMA2/FMUL2):
+// per pair of logits 2 FMUL2 + 2 FFMA2 + 2 MUFU + 1 cvt.  cy4[i] = (cyB[2i], cyB[2i+1],
+// yinv[2i], yinv[2i+1]).
+__device__ __forceinline__ void conv16_fast(const uint32_t (&v)[16], uint32_t* g, float c,
+                                            float offr, float R, const float4* cy4) {
+  const float2 c2 = make_float2(c, c), o2 = make_float2(-offr, -offr), r2 = make_float2(R, R);
 #pragma unroll
-  for (int e = 0; e < 32; e += 2) {
-    const float4 f = *reinterpret_cast<const float4*>(cy + e);  // (cyB0, yinv0, cyB1, yinv1)
-    const float e0 = ex2f(fmaf(__uint_as_float(v[e]) * f.y, c, -offr));
-    const float e1 = ex2f(fmaf(__uint_as_float(v[e + 1]) * f.w, c, -offr));
-    g[e >> 1] = pack_bf16x2(e0 * fmaf(R, f.x, f.y), e1 * fmaf(R, f.z, f.w));
+  for (int e = 0; e < 16; e += 2) {
+    const float4 f = cy4[e >> 1];
+    const float2 yi = make_float2(f.z, f.w);
+    const float2 t = __fmul2_rn(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), yi);
+    const float2 l = __ffma2_rn(t, c2, o2);
+    const float2 ex = make_float2(ex2f(l.x), ex2f(l.y));
+    const float2 w = __ffma2_rn(r2, make_float2(f.x, f.y), yi);
+    const float2 gg = __fmul2_rn(ex, w);
+    g[e >> 1] = pack_bf16x2(gg.x, gg.y);
   }
 }
 
@@ -153,8 +161,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
       mbar_init(&empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(&g_full[0], 128);
-    mbar_init(&g_full[1], 128);
+    mbar_init(&g_full[0], 256);
+    mbar_init(&g_full[1], 256);
     mbar_init(stg_full, 1);  // armed with expect_tx by the MMA issuer; bytes arrive via st.async
     mbar_init(stg_free, 1);
     mbar_init(acc_full, 1);
@@ -288,7 +296,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_ts(tm_acc, tm_s + (js >> 1) * 128 + (js & 1) * 32 + k * 8,
+            umma_ts(tm_acc, tm_s + (js * 2 + (k >> 1)) * 32 + (k & 1) * 8,
                     make_smem_desc_sw128(st + k * 2048, YSUB_BYTES, 1024), idesc_dx, accf);
             accf = 1;
           }
@@ -302,7 +310,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         begin_dx();
         TRACE(2, peer_cnt);
 #ifdef MMCL_NO_DSM  // timing experiment only (tools/bwd_trace.cu): no G exchange, wrong results
-        mbar_arrive_expect_tx(stg_full, 2 * 8 * 8 * 16);
+        mbar_arrive_expect_tx(stg_full, 8 * 8 * 16);
 #else
         mbar_arrive_expect_tx(stg_full, STG_BYTES);  // 128 rows x 512 B from the partner's st.async
 #endif
@@ -384,17 +392,23 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         const float offr = (p.off_row && grow < p.nx) ? fmaf(p.off_row[grow], p.off_mul, p.row_add) : INFINITY;
         const float cc = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
         const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
-        named_bar_sync(1 + 2 * wg, 128);  // the warpgroup is done with the previous column data
+        named_bar_sync(1, 256);  // everyone is done with the previous step's column data
         {
           const int j = wg * 128 + et;
           const int gy = yt * BNY + j;
           float2 v2;
           v2.x = (p.off_col && gy < p.ny) ? fmaf(p.off_col[gy], p.off_mul, p.col_add) : INFINITY;
           v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
-          if (fast) v2.x = ex2f(mu - v2.x) * v2.y;
-          sCol[j] = v2;
+          if (fast) {
+            // pair-planar layout for the packed-math path: (cyB0, cyB1, yinv0, yinv1)
+            float* f = reinterpret_cast<float*>(sCol) + (j >> 1) * 4 + (j & 1);
+            f[0] = ex2f(mu - v2.x) * v2.y;
+            f[2] = v2.y;
+          } else {
+            sCol[j] = v2;
+          }
         }
-        named_bar_sync(2 + 2 * wg, 128);
+        named_bar_sync(2, 256);
         mbar_wait(s_full, own_cnt & 1);
         tc_fence_after();
         if (lane == 0 && q == 0) TRACE(10 + wg, own_cnt);
@@ -402,22 +416,38 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         // on its staging buffer; nothing is read here, so CTA-scope acquire is enough)
         mbar_wait(stg_free, (own_cnt & 1) ^ 1);
         if (lane == 0 && q == 0) TRACE(12 + wg, own_cnt);
-#pragma unroll 1
-        for (int ch = wg * 4; ch < wg * 4 + 4; ++ch) {
-          uint32_t v[32], g[16];
-          tmem_ld_x32(tm_s + lane_base + ch * 32, v);
-          tmem_ld_wait();
+        // both warpgroups convert key half 0 first (chunks 0,1 | 2,3), then half 1 (4,5 | 6,7), so
+        // the dX MMAs of half 0 run under the conversion of half 1
+        // Software pipeline over 16-column halves: the tensor-memory load of the next half is
+        // in flight while the current one is converted.
+        uint32_t va[16], vb[16], g[16];
+        const uint32_t sbase = tm_s + lane_base;
+        auto convert = [&](const uint32_t (&v)[16], uint32_t* gout, int col) {
           if (fast)
-            g_chunk_fast(v, g, cc, offr, R, sCol + ch * 32);
+            conv16_fast(v, gout, cc, offr, R, reinterpret_cast<const float4*>(sCol) + (col >> 1));
           else if (mode == 3)
-            g_chunk<3>(v, g, cc, offr, sCol + ch * 32);
+            conv16<3>(v, gout, cc, offr, sCol + col);
           else if (mode == 1)
-            g_chunk<1>(v, g, cc, offr, sCol + ch * 32);
+            conv16<1>(v, gout, cc, offr, sCol + col);
           else
-            g_chunk<2>(v, g, cc, offr, sCol + ch * 32);
-          // G of key half h lives in S columns [128 h, 128 h + 64): inside the columns this
-          // warpgroup has already consumed
-          tmem_st_x16(tm_s + lane_base + wg * 128 + (ch & 3) * 16, g);
+            conv16<2>(v, gout, cc, offr, sCol + col);
+        };
+        tmem_ld_x16(sbase + uint32_t(wg * 2) * 32u, va);
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int ch = (ci >> 1) * 4 + wg * 2 + (ci & 1);
+          tmem_ld_wait();
+          tmem_ld_x16(sbase + ch * 32 + 16, vb);
+          convert(va, g, ch * 32);
+          tmem_ld_wait();
+          if (ci < 3) {
+            const int chn = ((ci + 1) >> 1) * 4 + wg * 2 + ((ci + 1) & 1);
+            tmem_ld_x16(sbase + chn * 32, va);
+          }
+          convert(vb, g + 8, ch * 32 + 16);
+          // G chunk ch overwrites the first 16 columns of S chunk ch (already consumed by this
+          // very thread), so no other warp's reads are ever at risk
+          tmem_st_x16(tm_s + lane_base + ch * 32, g);
           // The same 32 keys (64 B per row) go to the partner's staging tile (atom ch/2, 128-byte
           // swizzle, K-major).  Distributed-shared-memory stores are packet-rate bound, so the
           // warp first transposes through a 2 KB buffer: each st.async instruction then covers
@@ -443,15 +473,17 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
                          : "r"(xb + uint32_t(s2 * 512 + lane * 16))
                          : "memory");
 #ifdef MMCL_NO_DSM
-            if (s2 == 0 && (ch & 3) == 0 && lane < 8)  // 64 x 16 B... timing experiment only
+            if (s2 == 0 && ci == 0 && lane < 8)  // 8 warps x 8 lanes x 16 B: timing experiment only
 #endif
             st_async_v4(abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4), w0, w1, w2, w3,
                         peer_stg_full);
           }
+          if (ci & 1) {  // this warpgroup's share of key half ci/2 is in tensor memory
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&g_full[ci >> 1]);
+          }
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&g_full[wg]);  // this key half (128 columns) of G is complete
         if (lane == 0 && q == 0) TRACE(14 + wg, own_cnt);
         ++own_cnt;
       }
