@@ -100,6 +100,34 @@ int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_r
  * contrastive.py:431-578 (all-gather, and the reduce-scatter that autograd's all-gather
  * performs in backward, contrastive.py:506).
  * ------------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------
+ * Symmetric peer-memory arena (one node, CUDA IPC over NVLink / NVSwitch): the B200-native
+ * all-gather.  Every rank owns two equally sized buffers ("parity" 0 / 1) mapped by all ranks;
+ * a contribution is WRITTEN BY ITS PRODUCER KERNEL to the same offset of every rank's buffer,
+ * and mmcl_symm_fence orders it: work enqueued after the fence on the same stream sees what
+ * every rank wrote before its own fence.  The handle owns the arena.
+ *   mmcl_symm_reserve   collective, same size on all ranks; may synchronise the stream and the
+ *                       ranks when the arena has to be (re)allocated, otherwise returns at once
+ *   mmcl_symm_buffer    local address of buffer `parity` (tensor-map / kernel operand)
+ *   mmcl_symm_put       src[0:bytes) -> offset dst_off of every rank's buffer (4-byte units)
+ *   mmcl_pack_rows_symm mmcl_pack_rows with the stores fanned out to every rank
+ *                       (dst_off_inv < 0: no inverse norms)
+ *   mmcl_symm_fence     collective on the stream (one small kernel, no host involvement)
+ * Buffer reuse: alternate the parity between consecutive uses; a buffer may be overwritten once
+ * the caller has passed a later fence AND every rank enqueued its reads of that buffer before
+ * its own later fence.
+ * Replaces: the NCCL all-gathers of _gather_dicts (contrastive.py:431-499) on one node.
+ * ------------------------------------------------------------------------------------------ */
+int mmcl_symm_reserve(mmcl_handle* h, size_t bytes_per_buffer, mmcl_stream stream);
+int mmcl_symm_buffer(mmcl_handle* h, int parity, void** out, size_t* bytes);
+int mmcl_symm_put(mmcl_handle* h, int parity, const void* src, size_t bytes, size_t dst_off,
+                  mmcl_stream stream);
+int mmcl_pack_rows_symm(mmcl_handle* h, int parity, const void* src, int src_dtype,
+                        int64_t src_rows, int64_t d, const int64_t* idx, int64_t n_out,
+                        int normalize, size_t dst_off_rows, int64_t dst_off_inv,
+                        mmcl_stream stream);
+int mmcl_symm_fence(mmcl_handle* h, mmcl_stream stream);
+
 /* Bracket several collective calls so that NCCL launches them as one fused operation
  * (ncclGroupStart / ncclGroupEnd); no-ops for world == 1. */
 int mmcl_group_start(mmcl_handle* h);

@@ -28,6 +28,12 @@ SYMBOLS = {
                                     c_void_p, c_size_t, c_void_p]),
     "mmcl_pack_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64,
                                c_int, c_void_p, c_void_p, c_void_p]),
+    "mmcl_symm_reserve": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "mmcl_symm_buffer": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_size_t)]),
+    "mmcl_symm_put": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "mmcl_pack_rows_symm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
+                                    c_int64, c_int, c_size_t, c_int64, c_void_p]),
+    "mmcl_symm_fence": (c_int, [c_void_p, c_void_p]),
     "mmcl_group_start": (c_int, [c_void_p]),
     "mmcl_group_end": (c_int, [c_void_p]),
     "mmcl_all_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64,

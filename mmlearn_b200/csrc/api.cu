@@ -22,6 +22,7 @@ struct mmcl_handle {
   int world = 1;
   int num_sms = 0;
   ncclComm_t comm = nullptr;
+  SymmArena arena;
   std::mutex mu;
 };
 
@@ -115,6 +116,10 @@ int mmcl_create(mmcl_handle** out, int device, int rank, int world, const void* 
 
 int mmcl_destroy(mmcl_handle* h) {
   if (!h) return MMCL_OK;
+  {
+    DeviceGuard g(h->device);
+    symm_destroy(&h->arena, h->rank);
+  }
   if (h->comm) ncclCommDestroy(h->comm);
   delete h;
   return MMCL_OK;
@@ -185,6 +190,71 @@ int mmcl_group_end(mmcl_handle* h) {
   if (h->world == 1) return MMCL_OK;
   ncclResult_t r = ncclGroupEnd();
   return r == ncclSuccess ? MMCL_OK : nccl_fail(r, "ncclGroupEnd");
+}
+
+int mmcl_symm_reserve(mmcl_handle* h, size_t bytes_per_buffer, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_symm_reserve: null handle");
+  REQUIRE(h->world > 1 && h->world <= 32, "mmcl_symm_reserve: needs 2..32 ranks");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  std::string err;
+  if (symm_reserve(&h->arena, h->comm, h->rank, h->world, bytes_per_buffer,
+                   static_cast<cudaStream_t>(stream), &err))
+    return fail(MMCL_ERR_CUDA, "mmcl_symm_reserve: " + err);
+  return MMCL_OK;
+}
+
+int mmcl_symm_buffer(mmcl_handle* h, int parity, void** out, size_t* bytes) {
+  REQUIRE(h && out, "mmcl_symm_buffer: null argument");
+  REQUIRE(h->arena.local, "mmcl_symm_buffer: no arena reserved");
+  *out = symm_buffer(&h->arena, parity);
+  if (bytes) *bytes = h->arena.bytes;
+  return MMCL_OK;
+}
+
+int mmcl_symm_put(mmcl_handle* h, int parity, const void* src, size_t bytes, size_t dst_off,
+                  mmcl_stream stream) {
+  REQUIRE(h && h->arena.local, "mmcl_symm_put: no arena reserved");
+  REQUIRE(bytes % 4 == 0 && dst_off % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0,
+          "mmcl_symm_put: size, offset and source must be multiples of 4 bytes");
+  REQUIRE(dst_off + bytes <= h->arena.bytes, "mmcl_symm_put: beyond the reserved buffer");
+  REQUIRE(bytes == 0 || src, "mmcl_symm_put: null source");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_symm_put(&h->arena, h->world, parity, src, bytes, dst_off,
+                                  static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_symm_put");
+}
+
+int mmcl_pack_rows_symm(mmcl_handle* h, int parity, const void* src, int src_dtype,
+                        int64_t src_rows, int64_t d, const int64_t* idx, int64_t n_out,
+                        int normalize, size_t dst_off_rows, int64_t dst_off_inv,
+                        mmcl_stream stream) {
+  REQUIRE(h && h->arena.local, "mmcl_pack_rows_symm: no arena reserved");
+  REQUIRE(src_dtype >= 0 && src_dtype <= 2, "mmcl_pack_rows_symm: dtype must be f32/bf16/f16");
+  REQUIRE(d > 0 && d % 8 == 0, "mmcl_pack_rows_symm: d must be a positive multiple of 8");
+  REQUIRE(n_out >= 0 && src_rows >= 0, "mmcl_pack_rows_symm: negative size");
+  REQUIRE(n_out == 0 || src, "mmcl_pack_rows_symm: null source");
+  REQUIRE(dst_off_rows % 16 == 0 && dst_off_rows + size_t(n_out) * d * 2 <= h->arena.bytes,
+          "mmcl_pack_rows_symm: rows beyond the reserved buffer");
+  REQUIRE(dst_off_inv < 0 || (dst_off_inv % 4 == 0 &&
+                              size_t(dst_off_inv) + size_t(n_out) * 4 <= h->arena.bytes),
+          "mmcl_pack_rows_symm: inverse norms beyond the reserved buffer");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_pack_rows_symm(&h->arena, h->world, parity, src, src_dtype, src_rows, d,
+                                        idx, n_out, normalize, dst_off_rows, dst_off_inv,
+                                        static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_pack_rows_symm");
+}
+
+int mmcl_symm_fence(mmcl_handle* h, mmcl_stream stream) {
+  REQUIRE(h && h->arena.local, "mmcl_symm_fence: no arena reserved");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_symm_fence(&h->arena, h->world, h->rank,
+                                    static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_symm_fence");
 }
 
 int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int64_t* counts,

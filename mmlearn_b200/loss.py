@@ -18,7 +18,10 @@ log-sum-exp vectors cross NVLink in backward, never an [N,d] gradient.
 
 from __future__ import annotations
 
+import ctypes
 import math
+import os
+import weakref
 from typing import Optional
 
 import torch
@@ -26,7 +29,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import _lib
-from ._lib import check, counts_array, ptr
+from ._lib import MmclError, check, counts_array, ptr
 from .modalities import LossPairSpec, Modalities
 from .plan import PairPlan, all_gather_ints, dist_info
 
@@ -132,6 +135,111 @@ def find_matching_indices(first_example_ids: torch.Tensor, second_example_ids: t
     return m.finish(k)
 
 
+class _Raw:
+    """Raw device memory as a __cuda_array_interface__ object (uint8)."""
+
+    def __init__(self, ptr_: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
+                                         "data": (ptr_, False), "version": 2}
+
+
+class _ArenaState:
+    """Host-side bookkeeping of a handle's symmetric arena (include/mmcl.h, mmcl_symm_*): which
+    buffer (parity) the next forward uses and which run still reads each buffer."""
+
+    def __init__(self):
+        self.step = 0
+        self.owner = [None, None]  # weakref to the _Run whose saved tensors live in the buffer
+        self.disabled = os.environ.get("MMCL_NO_SYMM", "0") == "1"
+        self.views: dict = {}
+
+
+_ARENAS: dict = {}
+
+
+class _Transport:
+    """How one forward moves data between ranks: direct peer stores into the symmetric arena
+    (NVLink, one fence kernel, no NCCL launch) when it is available, NCCL all-gathers otherwise.
+    Every decision in here depends only on state that is identical on all ranks."""
+
+    def __init__(self, run, need_bytes: int):
+        self.run, self.lib, self.h, self.dev = run, _lib.load(), run.h, run.dev
+        self.world, self.rank = dist_info()
+        self.st = _stream(self.dev)
+        self.arena = False
+        self.pending = False
+        if self.world == 1:
+            return
+        key = self.h.value
+        a = _ARENAS.setdefault(key, _ArenaState())
+        if a.disabled:
+            return
+        parity = a.step & 1
+        prev = a.owner[parity]() if a.owner[parity] is not None else None
+        if prev is not None and prev is not run and prev.states:
+            return  # a run that was not back-propagated yet still reads this buffer: use NCCL
+        if self.lib.mmcl_symm_reserve(self.h, max(need_bytes, 1 << 20), self.st) != 0:
+            a.disabled = True  # agreed on by all ranks inside the call
+            return
+        out, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        check(self.lib.mmcl_symm_buffer(self.h, parity, ctypes.byref(out), ctypes.byref(nbytes)),
+              "mmcl_symm_buffer")
+        vkey = (parity, out.value, nbytes.value)
+        if vkey not in a.views:
+            a.views = {k_: v for k_, v in a.views.items() if k_[0] != parity}
+            a.views[vkey] = torch.as_tensor(_Raw(out.value, nbytes.value), device=self.dev)
+        self.base = a.views[vkey]
+        self.capacity = nbytes.value
+        self.parity = parity
+        self.cursor = 0
+        self.arena = True
+        a.step += 1
+        a.owner[parity] = weakref.ref(run)
+
+    # ---- arena primitives ----
+    def alloc(self, nbytes: int) -> int:
+        off = self.cursor
+        self.cursor = (off + nbytes + 1023) & ~1023
+        if self.cursor > self.capacity:
+            raise MmclError("symmetric arena overflow (internal sizing error)")
+        return off
+
+    def view(self, off: int, count: int, dtype, shape=None):
+        t = self.base[off:off + count * dtype.itemsize].view(dtype)
+        return t.view(shape) if shape is not None else t
+
+    def put(self, src: torch.Tensor, nbytes: int, dst_off: int) -> None:
+        if nbytes > 0:
+            check(self.lib.mmcl_symm_put(self.h, self.parity, ptr(src), nbytes, dst_off, self.st),
+                  "mmcl_symm_put")
+        self.pending = True
+
+    def fence(self) -> None:
+        if self.arena and self.pending:
+            check(self.lib.mmcl_symm_fence(self.h, self.st), "mmcl_symm_fence")
+            self.pending = False
+
+    # ---- gathers used by the loss ----
+    def gather_vector(self, loc: Optional[torch.Tensor], counts, itemsize: int, dtype, row_shape=()):
+        """All-gather of per-rank row blocks (counts[r] rows of `itemsize` bytes); returns the
+        gathered tensor.  With the arena the data is visible after the next fence()."""
+        n = sum(counts)
+        off_rows = sum(counts[:self.rank])
+        nloc = 0 if loc is None else min(loc.shape[0], counts[self.rank])
+        per = itemsize // dtype.itemsize
+        if self.arena:
+            off = self.alloc(n * itemsize)
+            self.put(loc, nloc * itemsize, off + off_rows * itemsize)
+            return self.view(off, n * per, dtype, (n, *row_shape) if row_shape else (n,))
+        full = torch.empty((n, *row_shape) if row_shape else (n,), dtype=dtype, device=self.dev)
+        if nloc:
+            full[off_rows:off_rows + nloc].copy_(loc[:nloc])
+        check(self.lib.mmcl_all_gather_rows(self.h, full.data_ptr() + off_rows * itemsize, ptr(full),
+                                            counts_array(counts), itemsize, self.st),
+              "mmcl_all_gather_rows")
+        return full
+
+
 class _PairState:
     """Everything one modality pair needs between forward and backward."""
 
@@ -207,6 +315,10 @@ class _Run:
         m._plan_cache[sig] = self.all_info
         return res
 
+    def release(self):
+        """Drop the saved state (and with it the claim on the symmetric arena buffer)."""
+        self.states = []
+
     def _forward_impl(self, assumed: Optional[torch.Tensor]):
         lib = _lib.load()
         m = self.m
@@ -243,11 +355,35 @@ class _Run:
                                       quick=quick))
             else:
                 matches.append(None)
+        # upper bound of what this forward keeps in the symmetric arena (rows + norms of both
+        # modalities, ids for the cross-rank check, log-sum-exp vectors, the table itself)
+        tab = assumed
+        need_bytes = 0
+        if world > 1 and tab is not None:
+            need_bytes = 4096 + world * P * 32
+            for p in range(P):
+                n_p = int(tab[:, p, 0].sum())
+                need_bytes += 2 * (n_p * d * 2 + n_p * 4) + 2 * n_p * 4 + 16 * 1024
+                need_bytes += int(tab[:, p, 2].sum() + tab[:, p, 3].sum()) * 16
+        tr = _Transport(self, need_bytes) if (world == 1 or tab is not None) else None
+
         # one exchange: the table of every rank (replaces contrastive.py:197-206 and the shape
         # gathers of _gather_all_tensors)
-        all_info_dev = all_gather_ints(info.view(-1), world).view(world, P, 4)
+        if tr is not None and tr.arena:
+            off_tab = tr.alloc(world * P * 32)
+            tr.put(info, P * 32, off_tab + rank * P * 32)
+            all_info_dev = tr.view(off_tab, world * P * 4, torch.long, (world, P, 4))
+        else:
+            all_info_dev = all_gather_ints(info.view(-1), world).view(world, P, 4)
         all_info = all_info_dev.cpu() if assumed is None else assumed  # host sync (first step)
         self.all_info = all_info
+        if tr is None:  # first step: the table has just been read, size the arena from it
+            need_bytes = 4096 + world * P * 32
+            for p in range(P):
+                n_p = int(all_info[:, p, 0].sum())
+                need_bytes += 2 * (n_p * d * 2 + n_p * 4) + 2 * n_p * 4 + 16 * 1024
+                need_bytes += int(all_info[:, p, 2].sum() + all_info[:, p, 3].sum()) * 16
+            tr = _Transport(self, need_bytes)
         verify: list = []  # (device scalar, expected int) pairs checked at the end (speculation)
         gcache: dict = {}
 
@@ -277,56 +413,70 @@ class _Run:
                 # else: the assumed table does not fit this rank's batch; the step is queued
                 # anyway (same collectives as every other rank) and fails verification
             all_ident = all(bool(all_info[r, p, 1]) or counts[r] == 0 for r in range(world))
+            gids = None
             if world > 1:
-                kg = self._global_match_count(ma, mb, ids_of, all_info[:, p, 2].tolist(),
-                                              all_info[:, p, 3].tolist(), gcache,
-                                              quick=assumed is not None and all(
-                                                  bool(all_info[r, p, 1]) and int(all_info[r, p, 0])
-                                                  == int(all_info[r, p, 2]) == int(all_info[r, p, 3])
-                                                  for r in range(world)))
-                if assumed is None:
-                    self._raise_if_cross_rank(ma, mb, int(kg.item()), n_total)
-                else:
-                    verify.append((kg, n_total))
+                quick_global = assumed is not None and all(
+                    bool(all_info[r, p, 1]) and int(all_info[r, p, 0]) == int(all_info[r, p, 2])
+                    == int(all_info[r, p, 3]) for r in range(world))
+                gids = self._global_ids(ma, mb, ids_of, all_info[:, p, 2].tolist(),
+                                        all_info[:, p, 3].tolist(), gcache, quick_global, tr)
 
             def gathered(key, idx, name):
                 """Raw bf16 rows of every rank's matched samples, [N, d], plus their fp32
                 inverse norms [N] (None without l2_normalize).  The local rows are packed
-                straight into their slot of the gather buffer; the all-gather is in place."""
+                straight into their slot of the gather buffer (of every rank, when the symmetric
+                arena is in use; otherwise an in-place NCCL all-gather follows)."""
                 ck = (key, "identity") if all_ident else None
                 if ck is not None and ck in shared:
                     return shared[ck]
                 src = self.embs[key] if key in self.embs else None
-                f_all = torch.empty(n_total, d, dtype=torch.bfloat16, device=dev)
-                inv_all = (torch.empty(n_total, dtype=torch.float32, device=dev)
-                           if m.l2_normalize else None)
-                if k > 0 and src is not None and src.shape[0] > 0:
-                    s_c = src.detach().contiguous()
-                    if s_c.dtype not in _DTYPES:
-                        raise ValueError(f"unsupported embedding dtype {s_c.dtype}")
-                    check(lib.mmcl_pack_rows(
-                        h, ptr(s_c), _DTYPES[s_c.dtype], s_c.shape[0], d, ptr(idx), k,
-                        int(m.l2_normalize), f_all.data_ptr() + plan.offset * d * 2,
-                        inv_all.data_ptr() + 4 * plan.offset if inv_all is not None else None, st),
-                        "mmcl_pack_rows")
-                if world > 1:
-                    check(lib.mmcl_all_gather_rows(h, f_all.data_ptr() + plan.offset * d * 2,
-                                                   ptr(f_all), counts_array(counts), d * 2, st),
-                          "mmcl_all_gather_rows")
-                    if inv_all is not None:
-                        check(lib.mmcl_all_gather_rows(h, inv_all.data_ptr() + 4 * plan.offset,
-                                                       ptr(inv_all), counts_array(counts), 4, st),
+                have = k > 0 and src is not None and src.shape[0] > 0
+                s_c = src.detach().contiguous() if have else None
+                if have and s_c.dtype not in _DTYPES:
+                    raise ValueError(f"unsupported embedding dtype {s_c.dtype}")
+                if tr.arena:
+                    off_rows = tr.alloc(n_total * d * 2)
+                    off_inv = tr.alloc(n_total * 4) if m.l2_normalize else -1
+                    f_all = tr.view(off_rows, n_total * d, torch.bfloat16, (n_total, d))
+                    inv_all = tr.view(off_inv, n_total, torch.float32) if m.l2_normalize else None
+                    if have:
+                        check(lib.mmcl_pack_rows_symm(
+                            h, tr.parity, ptr(s_c), _DTYPES[s_c.dtype], s_c.shape[0], d, ptr(idx), k,
+                            int(m.l2_normalize), off_rows + plan.offset * d * 2,
+                            off_inv + 4 * plan.offset if off_inv >= 0 else -1, st),
+                            "mmcl_pack_rows_symm")
+                    tr.pending = True
+                else:
+                    f_all = torch.empty(n_total, d, dtype=torch.bfloat16, device=dev)
+                    inv_all = (torch.empty(n_total, dtype=torch.float32, device=dev)
+                               if m.l2_normalize else None)
+                    if have:
+                        check(lib.mmcl_pack_rows(
+                            h, ptr(s_c), _DTYPES[s_c.dtype], s_c.shape[0], d, ptr(idx), k,
+                            int(m.l2_normalize), f_all.data_ptr() + plan.offset * d * 2,
+                            inv_all.data_ptr() + 4 * plan.offset if inv_all is not None else None,
+                            st), "mmcl_pack_rows")
+                    if world > 1:
+                        check(lib.mmcl_all_gather_rows(h, f_all.data_ptr() + plan.offset * d * 2,
+                                                       ptr(f_all), counts_array(counts), d * 2, st),
                               "mmcl_all_gather_rows")
+                        if inv_all is not None:
+                            check(lib.mmcl_all_gather_rows(h, inv_all.data_ptr() + 4 * plan.offset,
+                                                           ptr(inv_all), counts_array(counts), 4, st),
+                                  "mmcl_all_gather_rows")
                 if ck is not None:
                     shared[ck] = (f_all, inv_all)
                 return f_all, inv_all
 
-            if world > 1:
-                check(lib.mmcl_group_start(h), "mmcl_group_start")
             stt.fa_all, stt.inv_a = gathered(ma.embedding, stt.idx_a, ma.name)
             stt.fb_all, stt.inv_b = gathered(mb.embedding, stt.idx_b, mb.name)
+            tr.fence()  # arena: every rank's rows, norms, ids and table row are visible from here
             if world > 1:
-                check(lib.mmcl_group_end(h), "mmcl_group_end")
+                kg = self._global_match_count(ma, mb, gids, gcache)
+                if assumed is None:
+                    self._raise_if_cross_rank(ma, mb, int(kg.item()), n_total)
+                else:
+                    verify.append((kg, n_total))
             self.states.append(stt)
             if m.cache_labels:
                 m._remember_labels(plan, dev)
@@ -369,21 +519,19 @@ class _Run:
         # forward, so that backward issues no collective at all (a rank whose loss is a constant
         # 0 never runs backward; the reference deadlocks in that situation).
         if need_grad and world > 1:
-            check(lib.mmcl_group_start(h), "mmcl_group_start")
+            if not tr.arena:
+                check(lib.mmcl_group_start(h), "mmcl_group_start")
             for stt in self.states:
                 plan = stt.plan
                 if plan.col_denominators() is None:
                     continue
                 for name in ("lse_a", "lse_b"):
                     loc = getattr(stt, name, None) if plan.b_local > 0 else None
-                    full = torch.empty(plan.n_total, dtype=torch.float32, device=dev)
-                    if loc is not None:
-                        full[plan.offset:plan.offset + plan.b_local].copy_(loc)
-                    check(lib.mmcl_all_gather_rows(h, full.data_ptr() + 4 * plan.offset, ptr(full),
-                                                   counts_array(plan.counts), 4, st),
-                          "mmcl_all_gather_rows")
-                    setattr(stt, name + "_all", full)
-            check(lib.mmcl_group_end(h), "mmcl_group_end")
+                    setattr(stt, name + "_all",
+                            tr.gather_vector(loc, list(plan.counts), 4, torch.float32))
+            if not tr.arena:
+                check(lib.mmcl_group_end(h), "mmcl_group_end")
+        tr.fence()  # also covers a table-only step (no pair had rows)
         self.losses_present = losses_present
         if P == 1:
             loss, dscale = out2[0, 0], (out2[0, 1:2] if scale.numel() > 1 else out2[0, 1])
@@ -401,46 +549,40 @@ class _Run:
         return loss, dscale
 
     # ------------------------------------------------------------------------------------
-    def _global_match_count(self, ma, mb, ids_of, sizes_a, sizes_b, cache,
-                            quick: bool = False) -> torch.Tensor:
+    def _global_ids(self, ma, mb, ids_of, sizes_a, sizes_b, cache, quick: bool, tr):
+        """Gather the example ids the cross-rank check needs (see _global_match_count); with the
+        symmetric arena they become visible at the next fence."""
+        key = ("gids", ma.name, mb.name)
+        if key in cache:
+            return cache[key]
+        dev = self.dev
+
+        def gather_ids(name, sizes):
+            ck = ("ids", name)
+            if ck not in cache:
+                loc = (ids_of(name) if name in self.example_ids
+                       else torch.empty(0, 2, dtype=torch.long, device=dev))
+                cache[ck] = tr.gather_vector(loc, [int(x) for x in sizes], 16, torch.long, (2,))
+            return cache[ck]
+
+        # quick: every rank's local match is the identity (verified through the table), so the
+        # global match is the concatenation iff the gathered ids are all distinct
+        gb = gather_ids(mb.name, sizes_b)
+        ga = gb if quick else gather_ids(ma.name, sizes_a)
+        cache[key] = (ga, gb, quick)
+        return cache[key]
+
+    def _global_match_count(self, ma, mb, gids, cache) -> torch.Tensor:
         """Number of matches between the gathered id lists (device scalar, no host sync).
         The reference matches the *gathered* ids again (contrastive.py:310-313); the fused path
         needs the result only to confirm that the global match list is the concatenation of the
         local ones (true unless an example id occurs on two ranks)."""
-        lib = _lib.load()
         key = ("gcheck", ma.name, mb.name)
-        if key in cache:
-            return cache[key]
-        dev, h, st = self.dev, self.h, _stream(self.dev)
-        rank = dist.get_rank()
-
-        def gather_ids(name, sizes):
-            ck = ("ids", name)
-            if ck in cache:
-                return cache[ck]
-            sizes = [int(x) for x in sizes]
-            loc = ids_of(name) if name in self.example_ids else torch.empty(0, 2, dtype=torch.long,
-                                                                            device=dev)
-            full = torch.empty(sum(sizes), 2, dtype=torch.long, device=dev)
-            off = sum(sizes[:rank])
-            nloc = min(loc.shape[0], sizes[rank])  # differs only under a stale assumed table
-            if nloc:
-                full[off:off + nloc].copy_(loc[:nloc])
-            check(lib.mmcl_all_gather_rows(h, full.data_ptr() + off * 16, ptr(full),
-                                           counts_array(sizes), 16, st), "mmcl_all_gather_rows")
-            cache[ck] = full
-            return full
-
-        if quick:
-            # every rank's local match is the identity (verified through the table), so the
-            # global match is the concatenation iff the gathered ids are all distinct
-            gb = gather_ids(mb.name, sizes_b)
-            mt = _Match(h, gb, gb, quick=True)
-        else:
-            ga, gb = gather_ids(ma.name, sizes_a), gather_ids(mb.name, sizes_b)
-            mt = _Match(h, ga, gb, capacity=1)
-        cache[key] = mt.info[0]
-        cache[("keep", key)] = mt  # buffers stay alive until the kernels have run
+        if key not in cache:
+            ga, gb, quick = gids
+            mt = _Match(self.h, ga, gb, quick=True) if quick else _Match(self.h, ga, gb, capacity=1)
+            cache[key] = mt.info[0]
+            cache[("keep", key)] = mt  # buffers stay alive until the kernels have run
         return cache[key]
 
     @staticmethod
@@ -643,6 +785,8 @@ class ContrastiveLoss(nn.Module):
         run.need_grad = torch.is_grad_enabled() and (
             any(e.requires_grad for e in embs) or logit_scale.requires_grad)
         loss = _FusedContrastiveFn.apply(run, logit_scale, *embs)
+        if not run.need_grad:
+            run.release()  # nothing will be back-propagated: free the arena buffer for reuse
         if not run.losses_present:
             # no loss to compute (e.g. no paired data in batch): contrastive.py:151-158
             return torch.zeros((), device=logit_scale.device, dtype=embs[0].dtype)
