@@ -244,7 +244,7 @@ class _PairState:
     """Everything one modality pair needs between forward and backward."""
 
     __slots__ = ("plan", "key_a", "key_b", "idx_a", "idx_b", "fa_all", "fb_all", "inv_a", "inv_b",
-                 "lse_a", "lse_b", "lse_a_all", "lse_b_all", "scale_index", "pos")
+                 "lse_a", "lse_b", "lse_a_all", "lse_b_all", "scale_index", "pos", "dacc")
 
 
 class _FusedContrastiveFn(torch.autograd.Function):
@@ -338,6 +338,8 @@ class _Run:
                 ids[name] = t.to(device=dev, dtype=torch.long).contiguous()
             return ids[name]
 
+        # the table as plain Python ints: tensor element access costs microseconds apiece
+        assumed_l = assumed.tolist() if assumed is not None else None
         matches: list[Optional[_Match]] = []
         mods = []
         # per pair: [k, identity, rows of ids_a, rows of ids_b], written by the matcher itself
@@ -349,23 +351,27 @@ class _Run:
             if ma.embedding in self.embs and mb.embedding in self.embs:
                 _validate_ids(self.example_ids[ma.name], self.example_ids[mb.name])
                 # under an assumed table that says "identity here", only that is tested
-                quick = (assumed is not None and bool(assumed[rank, p, 1])
-                         and int(assumed[rank, p, 0]) > 0)
+                quick = (assumed is not None and bool(assumed_l[rank][p][1])
+                         and assumed_l[rank][p][0] > 0)
                 matches.append(_Match(h, ids_of(ma.name), ids_of(mb.name), info=info[p],
                                       quick=quick))
             else:
                 matches.append(None)
         # upper bound of what this forward keeps in the symmetric arena (rows + norms of both
         # modalities, ids for the cross-rank check, log-sum-exp vectors, the table itself)
-        tab = assumed
-        need_bytes = 0
-        if world > 1 and tab is not None:
-            need_bytes = 4096 + world * P * 32
+        def arena_bytes(T):
+            nb = 4096 + world * P * 32
             for p in range(P):
-                n_p = int(tab[:, p, 0].sum())
-                need_bytes += 2 * (n_p * d * 2 + n_p * 4) + 2 * n_p * 4 + 16 * 1024
-                need_bytes += int(tab[:, p, 2].sum() + tab[:, p, 3].sum()) * 16
-        tr = _Transport(self, need_bytes) if (world == 1 or tab is not None) else None
+                n_p = sum(T[r][p][0] for r in range(world))
+                nb += 2 * (n_p * d * 2 + n_p * 4) + 2 * n_p * 4 + 16 * 1024
+                nb += sum(T[r][p][2] + T[r][p][3] for r in range(world)) * 16
+            return nb
+
+        tr = None
+        if world == 1:
+            tr = _Transport(self, 0)
+        elif assumed_l is not None:
+            tr = _Transport(self, arena_bytes(assumed_l))
 
         # one exchange: the table of every rank (replaces contrastive.py:197-206 and the shape
         # gathers of _gather_all_tensors)
@@ -377,13 +383,9 @@ class _Run:
             all_info_dev = all_gather_ints(info.view(-1), world).view(world, P, 4)
         all_info = all_info_dev.cpu() if assumed is None else assumed  # host sync (first step)
         self.all_info = all_info
+        T = all_info.tolist() if assumed_l is None else assumed_l
         if tr is None:  # first step: the table has just been read, size the arena from it
-            need_bytes = 4096 + world * P * 32
-            for p in range(P):
-                n_p = int(all_info[:, p, 0].sum())
-                need_bytes += 2 * (n_p * d * 2 + n_p * 4) + 2 * n_p * 4 + 16 * 1024
-                need_bytes += int(all_info[:, p, 2].sum() + all_info[:, p, 3].sum()) * 16
-            tr = _Transport(self, need_bytes)
+            tr = _Transport(self, arena_bytes(T))
         verify: list = []  # (device scalar, expected int) pairs checked at the end (speculation)
         gcache: dict = {}
 
@@ -394,7 +396,7 @@ class _Run:
         losses_present = False
         for p, pair in enumerate(self.pairs):
             ma, mb = mods[p]
-            counts = [int(all_info[r, p, 0]) for r in range(world)]
+            counts = [T[r][p][0] for r in range(world)]
             n_total = sum(counts)
             if n_total == 0:
                 continue  # nobody has this pair: every rank skips it (contrastive.py:304-316)
@@ -404,7 +406,7 @@ class _Run:
             stt.plan, stt.key_a, stt.key_b = plan, ma.embedding, mb.embedding
             stt.scale_index = p if scale.numel() > 1 else 0
             k = plan.b_local
-            ident = bool(all_info[rank, p, 1]) and k > 0
+            ident = bool(T[rank][p][1]) and k > 0
             stt.idx_a = stt.idx_b = None
             if k > 0 and not ident:
                 if matches[p] is not None and not matches[p].quick and (
@@ -412,14 +414,14 @@ class _Run:
                     stt.idx_a, stt.idx_b = matches[p].finish(k)
                 # else: the assumed table does not fit this rank's batch; the step is queued
                 # anyway (same collectives as every other rank) and fails verification
-            all_ident = all(bool(all_info[r, p, 1]) or counts[r] == 0 for r in range(world))
+            all_ident = all(bool(T[r][p][1]) or counts[r] == 0 for r in range(world))
             gids = None
             if world > 1:
                 quick_global = assumed is not None and all(
-                    bool(all_info[r, p, 1]) and int(all_info[r, p, 0]) == int(all_info[r, p, 2])
-                    == int(all_info[r, p, 3]) for r in range(world))
-                gids = self._global_ids(ma, mb, ids_of, all_info[:, p, 2].tolist(),
-                                        all_info[:, p, 3].tolist(), gcache, quick_global, tr)
+                    bool(T[r][p][1]) and T[r][p][0] == T[r][p][2] == T[r][p][3]
+                    for r in range(world))
+                gids = self._global_ids(ma, mb, ids_of, [T[r][p][2] for r in range(world)],
+                                        [T[r][p][3] for r in range(world)], gcache, quick_global, tr)
 
             def gathered(key, idx, name):
                 """Raw bf16 rows of every rank's matched samples, [N, d], plus their fp32
@@ -539,9 +541,20 @@ class _Run:
             loss = out2[:, 0].sum()
             dscale = out2[:, 1].clone() if scale.numel() > 1 else out2[:, 1].sum()
 
+        self.grad_kernels_done = False
         if assumed is not None:
-            # ---- verification of the assumed table: the step's only host sync ----
-            got = torch.cat([all_info_dev.reshape(-1)] + [kg.reshape(1) for kg, _ in verify]).cpu()
+            # ---- verification of the assumed table: the step's only host wait ----
+            # The fresh table is copied to pinned memory behind the forward work; the gradient
+            # kernels are queued BEHIND that copy, so the device keeps working while the host
+            # waits for the copy (not for the whole stream), returns the loss and runs autograd.
+            got_dev = torch.cat([all_info_dev.reshape(-1)] + [kg.reshape(1) for kg, _ in verify])
+            got = torch.empty(got_dev.shape, dtype=torch.long, pin_memory=True)
+            got.copy_(got_dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            if need_grad and m.eager_backward:
+                self.launch_grad_kernels()
+            ev.synchronize()
             want = torch.cat([assumed.reshape(-1),
                               torch.tensor([e for _, e in verify], dtype=torch.long)])
             if not torch.equal(got, want):
@@ -595,24 +608,21 @@ class _Run:
                 "refuses it instead of silently computing something else.")
 
     # ------------------------------------------------------------------------------------
-    def backward(self, gout: torch.Tensor):
+    def launch_grad_kernels(self) -> None:
+        """The heavy half of backward: for every pair and side, dacc = sum_j G_ij * yinv_j * Y_j
+        (fused recompute kernel).  It depends on nothing that backward() receives, so a
+        speculative forward launches it right away: the device works on it while the host waits
+        for the table verification and walks through autograd."""
+        if self.grad_kernels_done:
+            return
+        self.grad_kernels_done = True
         lib = _lib.load()
         dev, h = self.dev, self.h
         st = _stream(dev)
-        m = self.m
-        gout = gout.detach().to(device=dev, dtype=torch.float32).contiguous()
-        grads32: dict = {}
-        direct: dict = {}
-        # how many (pair, side) terms feed each embedding tensor: a tensor fed by exactly one
-        # term through the identity row map gets its gradient written once, in its own dtype
-        n_terms: dict = {}
-        for stt in self.states:
-            if stt.plan.b_local > 0:
-                for key in (stt.key_a, stt.key_b):
-                    n_terms[key] = n_terms.get(key, 0) + 1
         for stt in self.states:
             plan = stt.plan
             k, n, off = plan.b_local, plan.n_total, plan.offset
+            stt.dacc = [None, None]
             if k == 0:
                 continue
             d = stt.fa_all.shape[1]
@@ -620,8 +630,6 @@ class _Run:
             fa = stt.fa_all[off:off + k]
             fb = stt.fb_all[off:off + k]
             cden = plan.col_denominators()
-
-            pc = plan.positive_coefficient()
             ia_loc = stt.inv_a[off:off + k] if stt.inv_a is not None else None
             ib_loc = stt.inv_b[off:off + k] if stt.inv_b is not None else None
             # column-term log-sum-exp vectors: all rows of S (gathered) / all columns of S
@@ -645,14 +653,11 @@ class _Run:
                 row_b = make_off(stt.lse_b, k, None, plan.row_denominator())
                 col_for_a = make_off(col_lse_for_a, n, den, 1.0)
                 col_for_b = make_off(col_lse_for_b, n, den, 1.0)
-            for (key, x, y_all, lse_row, lse_col, partner, inv, yinv, pinv, idx, side) in (
-                (stt.key_a, fa, stt.fb_all, stt.lse_a, col_lse_for_a, fb, ia_loc, stt.inv_b, ib_loc,
-                 stt.idx_a, 0),
-                (stt.key_b, fb, stt.fa_all, stt.lse_b, col_lse_for_b, fa, ib_loc, stt.inv_a, ia_loc,
-                 stt.idx_b, 1),
+            for (key, x, y_all, lse_row, lse_col, inv, yinv, side) in (
+                (stt.key_a, fa, stt.fb_all, stt.lse_a, col_lse_for_a, ia_loc, stt.inv_b, 0),
+                (stt.key_b, fb, stt.fa_all, stt.lse_b, col_lse_for_b, ib_loc, stt.inv_a, 1),
             ):
-                src = self.embs[key]
-                if not src.requires_grad:
+                if not self.embs[key].requires_grad:
                     continue
                 dacc = torch.empty(k, d, dtype=torch.float32, device=dev)
                 if uniform:
@@ -667,6 +672,44 @@ class _Run:
                     check(lib.mmcl_sim_grad_bwd(h, ptr(x), k, ptr(y_all), n, d, sp, ptr(inv),
                                                 ptr(yinv), ptr(o_row), ptr(o_col), ptr(dacc), st),
                           "mmcl_sim_grad_bwd")
+                stt.dacc[side] = dacc
+
+    def backward(self, gout: torch.Tensor):
+        lib = _lib.load()
+        dev, h = self.dev, self.h
+        st = _stream(dev)
+        m = self.m
+        self.launch_grad_kernels()
+        gout = gout.detach().to(device=dev, dtype=torch.float32).contiguous()
+        grads32: dict = {}
+        direct: dict = {}
+        # how many (pair, side) terms feed each embedding tensor: a tensor fed by exactly one
+        # term through the identity row map gets its gradient written once, in its own dtype
+        n_terms: dict = {}
+        for stt in self.states:
+            if stt.plan.b_local > 0:
+                for key in (stt.key_a, stt.key_b):
+                    n_terms[key] = n_terms.get(key, 0) + 1
+        for stt in self.states:
+            plan = stt.plan
+            k, off = plan.b_local, plan.offset
+            if k == 0:
+                continue
+            d = stt.fa_all.shape[1]
+            sp = self.scale.data_ptr() + 4 * stt.scale_index
+            fa = stt.fa_all[off:off + k]
+            fb = stt.fb_all[off:off + k]
+            pc = plan.positive_coefficient()
+            ia_loc = stt.inv_a[off:off + k] if stt.inv_a is not None else None
+            ib_loc = stt.inv_b[off:off + k] if stt.inv_b is not None else None
+            for (key, partner, inv, pinv, idx, side) in (
+                (stt.key_a, fb, ia_loc, ib_loc, stt.idx_a, 0),
+                (stt.key_b, fa, ib_loc, ia_loc, stt.idx_b, 1),
+            ):
+                src = self.embs[key]
+                dacc = stt.dacc[side]
+                if not src.requires_grad or dacc is None:
+                    continue
                 s_c = src.detach().contiguous()
                 is_direct = (idx is None and n_terms.get(key, 0) == 1 and k == src.shape[0]
                              and key not in grads32)
@@ -738,6 +781,9 @@ class ContrastiveLoss(nn.Module):
         # attributes, not buffers: nothing is added to state_dict
         self._plan_cache: dict = {}
         self.speculate = True
+        # under speculation, queue the gradient kernels at the end of forward (they need nothing
+        # from backward()); set to False if the loss is often evaluated without back-propagation
+        self.eager_backward = True
 
     def _remember_labels(self, plan: PairPlan, device) -> None:
         """contrastive.py:190-219: rebuild when the logit width changes or the device is new."""
