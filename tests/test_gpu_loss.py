@@ -66,7 +66,8 @@ def test_golden_single_process(name):
 
 
 @pytest.mark.parametrize("n,d,dtype", [(256, 512, torch.float32), (2048, 512, torch.bfloat16),
-                                       (1000, 768, torch.bfloat16), (4096, 1024, torch.float16)])
+                                       (1000, 768, torch.bfloat16), (4096, 1024, torch.float16),
+                                       (8192, 512, torch.bfloat16)])
 def test_vs_oracle(n, d, dtype):
     emb, ids = synthetic_inputs(n, d)
     ref = contrastive_oracle(emb, ids, 1 / 0.07, [OPair(("rgb", "text"))], l2_normalize=True,
@@ -157,3 +158,78 @@ def test_cached_plan_speculation():
     ids3 = {k: v[:300] for k, v in ids[0].items()}
     check(ids3, emb3)
     check(ids[0], emb[0])
+
+
+def test_full_size_config2_against_torch_fp32():
+    """BASELINE config 2 at full size (N = 32768, d = 512, one GPU).  The CPU oracle cannot finish
+    this in seconds, so the check is (a) the loss against a chunked fp32 torch evaluation of the
+    same bf16-rounded inputs on the device, (b) size-independent properties of the gradients:
+    rows of d(loss)/d(x) are orthogonal to x (the loss only sees x/|x|), the two directions are
+    symmetric (swapping the modalities swaps the gradients), and the gradient norms match the
+    torch evaluation on a sample of 256 rows."""
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    n, d, s = 32768, 512, 1 / 0.07
+    g = torch.Generator().manual_seed(1234)
+    xa = torch.randn(n, d, generator=g)
+    xb = 0.5 * xa + torch.randn(n, d, generator=g)
+    a = xa.to(torch.bfloat16).to(DEV).requires_grad_(True)
+    b = xb.to(torch.bfloat16).to(DEV).requires_grad_(True)
+    ids = torch.stack([torch.zeros(n, dtype=torch.long), torch.arange(n)], 1).to(DEV)
+    sc = torch.tensor(s, device=DEV, requires_grad=True)
+    fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    loss = fn({"rgb_embedding": a, "text_embedding": b}, {"rgb": ids, "text": ids}, sc,
+              [LossPairSpec(("rgb", "text"))])
+    loss.backward()
+    torch.cuda.synchronize()
+    # (a) chunked fp32 reference of loss and d(scale)
+    ah = torch.nn.functional.normalize(a.detach().float(), dim=-1)
+    bh = torch.nn.functional.normalize(b.detach().float(), dim=-1)
+    lse_a = torch.empty(n, device=DEV)
+    lse_b = torch.empty(n, device=DEV)
+    for i in range(0, n, 4096):
+        lse_a[i:i + 4096] = torch.logsumexp(s * ah[i:i + 4096] @ bh.T, dim=1)
+        lse_b[i:i + 4096] = torch.logsumexp(s * bh[i:i + 4096] @ ah.T, dim=1)
+    pos = s * (ah * bh).sum(1)
+    ref = float((lse_a + lse_b - 2 * pos).mean() / 2)
+    assert float(loss) == pytest.approx(ref, rel=1e-3)
+    # (b1) gradient rows orthogonal to the input rows
+    for x in (a, b):
+        gx = x.grad.float()
+        cosang = (gx * x.detach().float()).sum(1) / (gx.norm(dim=1) * x.detach().float().norm(dim=1))
+        assert float(cosang.abs().max()) < 2e-2
+    # (b2) sampled rows against torch autograd on the same rows' loss terms
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(5))[:256].to(DEV)
+    a32 = a.detach().float().requires_grad_(True)
+    b32 = b.detach().float()
+    an = torch.nn.functional.normalize(a32, dim=-1)
+    bn = torch.nn.functional.normalize(b32, dim=-1)
+    # terms of the loss that depend on rows idx of a: their own rows of direction a, and
+    # column idx of every row of direction b
+    la = torch.logsumexp(s * an[idx] @ bn.T, dim=1) - s * (an[idx] * bn[idx]).sum(1)
+    part = la.sum() / (2 * n)
+    colterm = 0
+    for i in range(0, n, 8192):
+        sb = s * bn[i:i + 8192] @ an.T            # [chunk, n]
+        p = torch.exp(sb - lse_b[i:i + 8192, None])  # softmax with the reference lse (constant)
+        colterm = colterm + (p[:, idx].detach() * sb[:, idx]).sum()
+    part = part + colterm / (2 * n) - (s * (an[idx] * bn[idx]).sum(1)).sum() / (2 * n)
+    (gref,) = torch.autograd.grad(part, a32)
+    got, want = a.grad.float()[idx], gref[idx]
+    assert float(got.norm()) == pytest.approx(float(want.norm()), rel=1e-2)
+    assert float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0)) > 0.999
+
+
+def test_single_cta_backward_kernel_still_matches():
+    """The CTA-pair backward is the default; MMCL_BWD_SINGLE=1 selects the single-CTA kernel.
+    Run the kernel-level backward tests once more in a subprocess with that switch."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MMCL_BWD_SINGLE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_kernels.py", "-q", "-x",
+                        "-k", "sim_grad_bwd", "-m", "gpu"], cwd=root, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]

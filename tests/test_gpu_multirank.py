@@ -13,8 +13,11 @@ from tests.golden_util import case_names, load_case
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, name, init_file, ret):
+def _worker(rank, world, name, init_file, ret, no_symm=False):
     import torch.distributed as dist
+
+    if no_symm:
+        os.environ["MMCL_NO_SYMM"] = "1"  # NCCL all-gathers instead of the peer-memory arena
 
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -127,3 +130,24 @@ def test_speculation_sequence_two_ranks():
                     assert float(g.norm()) == 0
                     continue
                 assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2), (name, k)
+
+
+def test_nccl_transport_two_ranks():
+    """The same golden case through the NCCL all-gather path (MMCL_NO_SYMM=1); the default path
+    of the other tests is the symmetric peer-memory arena."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    name = "w2_uneven"
+    case = load_case(name)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker, args=(2, name, os.path.join(td, "init"), ret, True), nprocs=2, join=True)
+    for r in range(2):
+        ref, got = case["out"][r], ret[r]
+        assert got["loss"] == pytest.approx(float(ref["loss"]), rel=1e-3, abs=1e-6)
+        for k in [k for k in got if k.startswith("grad_")]:
+            g, e = torch.from_numpy(got[k]), torch.from_numpy(ref[k])
+            assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2)
