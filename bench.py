@@ -197,21 +197,26 @@ def main():
     l0 = lib.mmcl_kernel_launches()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
+    # No host synchronisation between the timed iterations (the bracket is around all K of
+    # them): the host runs ahead exactly as it does inside a training step.  The L2 flush is a
+    # kernel on the same stream, outside each iteration's event pair.
+    span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    span[0].record()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed iterations (outside the events)
-        barrier()
         ev[i][0].record()
         loss = one_step(d_a, d_b, d_ids, d_log_s)
         ev[i][1].record()
+    span[1].record()
     barrier()
     launches = (lib.mmcl_kernel_launches() - l0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, span[0].elapsed_time(span[1])], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t) / args.steps
+    ms_per_step = float(t[0]) / args.steps
+    ms_per_step_with_flush = float(t[1]) / args.steps
     value = N / (ms_per_step * 1e-3)
     loss_value = float(loss.detach())
 
@@ -222,8 +227,9 @@ def main():
            for _ in range(e2e_steps)]
     for i in range(e2e_steps + 2):
         j = i - 2
+        if j == 0:
+            barrier()
         flush.fill_(i & 0xFF)
-        barrier()
         if j >= 0:
             ev2[j][0].record()
         a = h_a.to(dev, non_blocking=True).requires_grad_(True)
@@ -234,6 +240,9 @@ def main():
         out_host.copy_(torch.stack([loss.detach(), log_s.grad]), non_blocking=True)
         if j >= 0:
             ev2[j][1].record()
+        # the user reads the loss on the host every step (logging): wait for the D2H copy
+        torch.cuda.current_stream(dev).synchronize()
+        e2e_loss = float(out_host[0])
     barrier()
     ms2 = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
     t2 = torch.tensor([ms2], device=dev, dtype=torch.float64)
@@ -306,7 +315,9 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"ContrastiveLoss fwd+bwd, global batch {N}, d={d}, 1 pair, "
                                    "l2_normalize+local_loss+gather_with_grad (BASELINE config 2)",
-                       "rows_per_gpu": b, "l2": "flushed between timed iterations (256 MiB write)",
+                       "rows_per_gpu": b, "l2": "flushed between timed iterations (256 MiB fill kernel on the stream, "
+                             "outside each iteration's event pair; no host sync between iterations)",
+                       "ms_per_step_incl_flush": ms_per_step_with_flush,
                        "parallelism": f"dp{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},

@@ -217,6 +217,85 @@ int mmcl_unpack_grad(mmcl_handle* h, const float* dacc, const void* partner_bf16
                      int normalize, const int64_t* idx, void* grad, int grad_dtype, int direct,
                      mmcl_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Steady-state step executor: one call enqueues the whole forward (and the heavy half of the
+ * backward) of the loss for the common case "same batch structure as the previous step":
+ * every pair present on every rank, every local id match the identity, the same number of rows
+ * `rows` on every rank.  It issues exactly the launches the caller would issue one by one
+ * through the entry points above (identity checks, pack, peer stores + fences, the two fused
+ * similarity passes per pair, positive logits, pair loss, log-sum-exp exchange, recompute
+ * backward), but from native code: the host cost of a step drops from ~1 ms of interpreter time
+ * to a few tens of microseconds, which is what bounds the step at 8 GPUs (rows = N/8).
+ * The assumption is VERIFIED, not trusted: the fresh id-match table of all ranks (and the
+ * cross-rank duplicate check) is copied to pinned host memory behind the forward work and
+ * mmcl_step_verify() compares it with the assumed one after waiting for that copy only; on a
+ * mismatch (on any rank -- all ranks see the same table) the caller discards the step and
+ * re-runs it through the general path.
+ * Replaces: the per-step Python control flow of ContrastiveLoss.forward (contrastive.py:59-160)
+ * and of autograd's backward for the steady-state case.
+ *
+ * Coefficients (den = denominators of the row / column softmax terms, pos_coef, loss_rows) are
+ * supplied by the caller (mmlearn_b200/plan.py is their single source).
+ * world > 1 needs the symmetric arena (mmcl_symm_reserve with >= mmcl_step_arena_bytes, then
+ * pass the parity of the buffer this step may use).  The caller owns `workspace`
+ * (mmcl_step_workspace_bytes; must stay alive until mmcl_step_backward has been enqueued) and
+ * reads results at the offsets mmcl_step_layout reports.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t mod_a, mod_b;   /* indices into the step's modality list */
+  int32_t scale_index;    /* entry of `scales` this pair uses */
+  int32_t has_col;        /* 1: column-softmax term present (keys carry gradient) */
+  double weight;          /* pair weight (LossPairSpec.weight) */
+  double loss_rows;       /* divisor of the cross-entropy mean */
+  double row_den, col_den;
+  double pos_coef;        /* coefficient of the positive-label term */
+} mmcl_step_pair;
+
+typedef struct {
+  int32_t n_modalities, n_pairs;
+  int32_t normalize;        /* l2_normalize */
+  int32_t all_reduce_loss;  /* world > 1 and not local_loss: sum the pair losses over ranks */
+  int32_t need_grad;        /* save state / exchange log-sum-exps for backward */
+  int32_t reserved;
+  int64_t rows;             /* matched rows per rank (identical on all ranks) */
+  int64_t d;
+  const int32_t* mod_dtype;      /* [n_modalities] mmcl_dtype of each embedding tensor */
+  const int32_t* mod_needs_grad; /* [n_modalities] */
+  const mmcl_step_pair* pairs;   /* [n_pairs] */
+} mmcl_step_desc;
+
+typedef struct {
+  size_t off_out2;   /* float [n_pairs][2]: (loss, d loss / d scale) per pair */
+  size_t off_vec;    /* float [n_pairs][5][rows]: lse_a, lse_b, esum_a, esum_b, pos */
+  size_t off_info;   /* int64 [n_pairs][4]: this rank's fresh match-table rows */
+} mmcl_step_layout_t;
+
+typedef struct mmcl_step mmcl_step;
+
+int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out);
+int mmcl_step_destroy(mmcl_step* s);
+size_t mmcl_step_workspace_bytes(const mmcl_step* s);
+size_t mmcl_step_arena_bytes(const mmcl_step* s);
+int mmcl_step_layout(const mmcl_step* s, mmcl_step_layout_t* out);
+/* emb[m] / ids[m]: device pointers of modality m ([rows,d] in mod_dtype[m]; int64 [rows,2]).
+ * local_ok == 0: this rank's batch does not have the assumed structure; it only goes through
+ * the collective motions (table row marked invalid, fences) so that every rank fails
+ * verification together.  launch_grad != 0 also enqueues the recompute-backward kernels. */
+int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const* emb,
+                      const int64_t* const* ids, const float* scales, void* workspace,
+                      int launch_grad, mmcl_stream stream);
+/* Waits for the table copy of the last mmcl_step_forward (not for the stream) and compares. */
+int mmcl_step_verify(mmcl_step* s, int* ok);
+/* The recompute-backward kernels alone (when mmcl_step_forward ran with launch_grad == 0). */
+int mmcl_step_grad_kernels(mmcl_step* s, int parity, const float* scales, void* workspace,
+                           mmcl_stream stream);
+/* grads[m]: gradient buffer of modality m or NULL; grad_direct[m] != 0: the modality receives
+ * exactly one term -> plain stores in mod_dtype[m]; otherwise fp32 accumulation (zeroed by the
+ * caller).  Must follow mmcl_step_forward(launch_grad) / mmcl_step_grad_kernels. */
+int mmcl_step_backward(mmcl_step* s, int parity, const void* const* emb, const float* scales,
+                       void* workspace, const float* gout, void* const* grads,
+                       const int32_t* grad_direct, mmcl_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,10 +7,36 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t,
+                    c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmcl.so")
+
+
+
+class StepPair(Structure):
+    """mmcl_step_pair (include/mmcl.h)."""
+
+    _fields_ = [("mod_a", c_int32), ("mod_b", c_int32), ("scale_index", c_int32),
+                ("has_col", c_int32), ("weight", c_double), ("loss_rows", c_double),
+                ("row_den", c_double), ("col_den", c_double), ("pos_coef", c_double)]
+
+
+class StepDesc(Structure):
+    """mmcl_step_desc (include/mmcl.h)."""
+
+    _fields_ = [("n_modalities", c_int32), ("n_pairs", c_int32), ("normalize", c_int32),
+                ("all_reduce_loss", c_int32), ("need_grad", c_int32), ("reserved", c_int32),
+                ("rows", c_int64), ("d", c_int64), ("mod_dtype", POINTER(c_int32)),
+                ("mod_needs_grad", POINTER(c_int32)), ("pairs", POINTER(StepPair))]
+
+
+class StepLayout(Structure):
+    """mmcl_step_layout_t (include/mmcl.h)."""
+
+    _fields_ = [("off_out2", c_size_t), ("off_vec", c_size_t), ("off_info", c_size_t)]
+
 
 #: every symbol include/mmcl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -60,6 +86,17 @@ SYMBOLS = {
     "mmcl_unpack_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
                                  c_double, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmcl_step_create": (c_int, [c_void_p, POINTER(StepDesc), POINTER(c_void_p)]),
+    "mmcl_step_destroy": (c_int, [c_void_p]),
+    "mmcl_step_workspace_bytes": (c_size_t, [c_void_p]),
+    "mmcl_step_arena_bytes": (c_size_t, [c_void_p]),
+    "mmcl_step_layout": (c_int, [c_void_p, POINTER(StepLayout)]),
+    "mmcl_step_forward": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p),
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "mmcl_step_verify": (c_int, [c_void_p, POINTER(c_int)]),
+    "mmcl_step_grad_kernels": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmcl_step_backward": (c_int, [c_void_p, c_int, POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                   POINTER(c_void_p), POINTER(c_int32), c_void_p]),
 }
 
 NCCL_UID_BYTES = 128

@@ -11,56 +11,15 @@
 #include <vector>
 #include <atomic>
 
-#include "../../include/mmcl.h"
-#include "kernels.h"
+#include "handle.h"
 
 using namespace mmcl;
 
-struct mmcl_handle {
-  int device = 0;
-  int rank = 0;
-  int world = 1;
-  int num_sms = 0;
-  ncclComm_t comm = nullptr;
-  SymmArena arena;
-  std::mutex mu;
-};
-
-namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-int cuda_fail(cudaError_t e, const char* where) {
-  return fail(MMCL_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
-}
-int nccl_fail(ncclResult_t r, const char* where) {
-  return fail(MMCL_ERR_NCCL, std::string(where) + ": " + ncclGetErrorString(r));
-}
-
-#define REQUIRE(cond, msg) \
-  do {                     \
-    if (!(cond)) return fail(MMCL_ERR_INVALID, msg); \
-  } while (0)
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
-}  // namespace
-
 namespace mmcl {
+std::string& last_error_slot() {
+  thread_local std::string g_err;
+  return g_err;
+}
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
@@ -72,7 +31,7 @@ int mmcl_version(void) { return MMCL_VERSION; }
 
 int64_t mmcl_kernel_launches(void) { return launches_so_far(); }
 
-const char* mmcl_last_error(void) { return g_err.c_str(); }
+const char* mmcl_last_error(void) { return last_error_slot().c_str(); }
 
 int mmcl_nccl_unique_id(void* uid) {
   REQUIRE(uid, "mmcl_nccl_unique_id: null uid");

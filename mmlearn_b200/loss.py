@@ -32,9 +32,11 @@ from . import _lib
 from ._lib import MmclError, check, counts_array, ptr
 from .modalities import LossPairSpec, Modalities
 from .plan import PairPlan, all_gather_ints, dist_info
+from .steady import SteadyPlan, table_rows
 
 _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _HANDLES: dict = {}
+_GENERAL = object()  # _forward_steady: "take the general path" (decided identically on all ranks)
 
 
 def _stream(dev) -> int:
@@ -304,20 +306,107 @@ class _Run:
         # a rank whose local batch no longer fits the table still goes through the motions and
         # the verification (which sees every rank's fresh table) fails on all ranks together.
         sig = (world, tuple(tuple(pr.modalities) for pr in self.pairs), bool(self.need_grad))
+        self.fast = None
         assumed = m._plan_cache.get(sig) if m.speculate else None
         if assumed is not None:
-            res = self._forward_impl(assumed)
+            res = _GENERAL
+            sp = m._steady.get(sig) if m.native_step else None
+            # (shared state only) the steady plan was built for these weights / scale layout
+            if sp is not None and sp.shared_key == self._shared_key():
+                res = self._forward_steady(sp, assumed)
+            if res is _GENERAL:
+                res = self._forward_impl(assumed)
             if res is not None:
                 return res
             self.states = []  # mis-speculation: fall through to the synchronous path
+            self.fast = None
             m._plan_cache.pop(sig, None)
+            m._steady.pop(sig, None)
         res = self._forward_impl(None)
         m._plan_cache[sig] = self.all_info
+        m._steady[sig] = self._build_steady() if m.native_step else None
         return res
+
+    def _shared_key(self):
+        """What a steady plan depends on besides the match table; identical on all ranks."""
+        m = self.m
+        return (tuple(float(pr.weight) for pr in self.pairs), int(self.scale.numel()),
+                m.l2_normalize, m.local_loss, m.gather_with_grad)
+
+    def _build_steady(self) -> Optional[SteadyPlan]:
+        """After a successful general step: if its match table describes the steady state (every
+        pair everywhere, identity matches, equal row counts), prepare the native step executor
+        for the following steps (mmlearn_b200/steady.py)."""
+        world, rank = dist_info()
+        P = len(self.pairs)
+        if P == 0:
+            return None
+        rows = table_rows(self.all_info.tolist(), world, P)
+        if rows is None:
+            return None
+        if world > 1:
+            a = _ARENAS.get(self.h.value)
+            if a is None or a.disabled:  # agreed on by all ranks (mmcl_symm_reserve)
+                return None
+        names, pair_mods = [], []
+        for pair in self.pairs:
+            idx = []
+            for name in pair.modalities:
+                nm = Modalities.get_modality(name).name
+                if nm not in names:
+                    names.append(nm)
+                idx.append(names.index(nm))
+            pair_mods.append(tuple(idx))
+        es = [self.embs.get(Modalities.get_modality(n).embedding) for n in names]
+        if any(e is None or e.dtype not in _DTYPES for e in es):
+            return None  # cannot happen with this table; stay on the general path
+        sp = SteadyPlan(self.h, world, rank, rows, es[0].shape[-1], names,
+                        [_DTYPES[e.dtype] for e in es], [bool(e.requires_grad) for e in es],
+                        self.pairs, pair_mods, int(self.scale.numel()), self.m.l2_normalize,
+                        self.m.local_loss, self.m.gather_with_grad, bool(self.need_grad))
+        sp.shared_key = self._shared_key()
+        return sp
+
+    def _forward_steady(self, sp: SteadyPlan, assumed: torch.Tensor):
+        """Speculative step through the native executor; None = mis-speculation, _GENERAL = the
+        symmetric arena is not available for this step (same decision on every rank)."""
+        m = self.m
+        world, rank = dist_info()
+        dev = self.dev
+        tr = _Transport(self, sp.arena_bytes)
+        if world > 1 and not tr.arena:
+            return _GENERAL
+        for pair in self.pairs:  # same argument errors as the general path / the reference
+            ma = Modalities.get_modality(pair.modalities[0])
+            mb = Modalities.get_modality(pair.modalities[1])
+            if ma.name in self.example_ids and mb.name in self.example_ids:
+                _validate_ids(self.example_ids[ma.name], self.example_ids[mb.name])
+        local_ok, es, ids = sp.local_inputs(self.embs, self.example_ids, dev)
+        if local_ok:
+            local_ok = [bool(self.embs[md.embedding].requires_grad) for md in sp.mods] == [
+                bool(x) for x in sp.needs_grad]
+        ws = torch.empty(sp.ws_bytes, dtype=torch.uint8, device=dev)
+        parity = tr.parity if world > 1 else 0
+        launch_grad = bool(self.need_grad and m.eager_backward)
+        self.states = [sp]  # claims the arena buffer until backward() / release()
+        if not sp.forward(parity, local_ok, es, ids, self.scale, ws, launch_grad, _stream(dev)):
+            return None
+        self.fast = (sp, parity, es, ws)
+        m.steady_steps += 1
+        self.grad_kernels_done = launch_grad
+        self.all_info = assumed
+        self.losses_present = True
+        P = sp.P
+        out2 = ws[sp.off_out2:sp.off_out2 + 8 * P].view(torch.float32).view(P, 2)
+        if P == 1:
+            return out2[0, 0], (out2[0, 1:2] if self.scale.numel() > 1 else out2[0, 1])
+        return out2[:, 0].sum(), (out2[:, 1].clone() if self.scale.numel() > 1
+                                  else out2[:, 1].sum())
 
     def release(self):
         """Drop the saved state (and with it the claim on the symmetric arena buffer)."""
         self.states = []
+        self.fast = None
 
     def _forward_impl(self, assumed: Optional[torch.Tensor]):
         lib = _lib.load()
@@ -674,7 +763,31 @@ class _Run:
                           "mmcl_sim_grad_bwd")
                 stt.dacc[side] = dacc
 
+    def _backward_steady(self, gout: torch.Tensor):
+        sp, parity, es, ws = self.fast
+        dev = self.dev
+        st = _stream(dev)
+        if not self.grad_kernels_done:
+            sp.grad_kernels(parity, self.scale, ws, st)
+            self.grad_kernels_done = True
+        gout = gout.detach().to(device=dev, dtype=torch.float32).contiguous()
+        by_key = dict(zip((md.embedding for md in sp.mods),
+                          sp.backward(parity, es, self.scale, ws, gout, st)))
+        out = []
+        for key in self.keys:
+            src = self.embs[key]
+            if not src.requires_grad:
+                out.append(None)
+            elif by_key.get(key) is not None:
+                out.append(by_key[key])
+            else:
+                out.append(torch.zeros_like(src))
+        self.release()
+        return out
+
     def backward(self, gout: torch.Tensor):
+        if self.fast is not None:
+            return self._backward_steady(gout)
         lib = _lib.load()
         dev, h = self.dev, self.h
         st = _stream(dev)
@@ -781,6 +894,10 @@ class ContrastiveLoss(nn.Module):
         # attributes, not buffers: nothing is added to state_dict
         self._plan_cache: dict = {}
         self.speculate = True
+        # steady-state steps go through the native step executor (mmlearn_b200/steady.py)
+        self._steady: dict = {}
+        self.steady_steps = 0  # diagnostic: forwards that went through the native executor
+        self.native_step = os.environ.get("MMCL_NO_NATIVE_STEP", "0") != "1"
         # under speculation, queue the gradient kernels at the end of forward (they need nothing
         # from backward()); set to False if the loss is often evaluated without back-propagation
         self.eager_backward = True

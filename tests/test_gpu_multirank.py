@@ -102,6 +102,7 @@ def _worker_sequence(rank, world, names, init_file, ret):
         out = {"loss": float(loss.detach())}
         for k, v in leaves.items():
             out[f"grad_{k}"] = (v.grad if v.grad is not None else torch.zeros_like(v)).float().cpu().numpy()
+        out["steady_steps"] = fn.steady_steps
         outs.append(out)
     ret[rank] = outs
     dist.barrier()
@@ -151,3 +152,55 @@ def test_nccl_transport_two_ranks():
         for k in [k for k in got if k.startswith("grad_")]:
             g, e = torch.from_numpy(got[k]), torch.from_numpy(ref[k])
             assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2)
+
+
+def _check_sequence(names, ret, want_steady):
+    for r in range(2):
+        for step, (name, got) in enumerate(zip(names, ret[r])):
+            ref = load_case(name)["out"][r]
+            assert got["loss"] == pytest.approx(float(ref["loss"]), rel=1e-3, abs=1e-6), (name, step)
+            for k in [k for k in got if k.startswith("grad_")]:
+                g, e = torch.from_numpy(got[k]), torch.from_numpy(ref[k])
+                if float(e.norm()) == 0:
+                    assert float(g.norm()) == 0, (name, step, k)
+                    continue
+                assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2), (name, step, k)
+                assert float(torch.nn.functional.cosine_similarity(
+                    g.flatten(), e.flatten(), dim=0)) > 0.999, (name, step, k)
+        assert [o["steady_steps"] for o in ret[r]] == want_steady, r
+
+
+@pytest.mark.parametrize("name", ["w2_ll0_gg0", "w2_ll0_gg1", "w2_ll1_gg0", "w2_ll1_gg1"])
+def test_native_step_two_ranks(name):
+    """Steps 2 and 3 of an unchanged batch structure run through the native step executor
+    (mmcl_step_*: peer stores into the symmetric arena, fences, no NCCL on the data path) and
+    must reproduce the golden outputs of the reference in all four flag modes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    names = [name] * 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_sequence, args=(2, names, os.path.join(td, "init"), ret), nprocs=2,
+                 join=True)
+    _check_sequence(names, ret, [0, 1, 2])
+
+
+def test_native_step_structure_change_on_one_rank():
+    """Rank 1's batch loses its pairs while rank 0's stays the same: rank 0 alone could not
+    notice, but the table every rank verifies holds every rank's fresh row, so both ranks leave
+    the native path together (and return to it once the structure is steady again)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    names = ["w2_ll1_gg0", "w2_ll1_gg0", "w2_rank1_unpaired", "w2_rank1_unpaired", "w2_ll1_gg0",
+             "w2_ll1_gg0", "w2_ll1_gg0"]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_sequence, args=(2, names, os.path.join(td, "init"), ret), nprocs=2,
+                 join=True)
+    _check_sequence(names, ret, [0, 1, 1, 1, 1, 2, 3])

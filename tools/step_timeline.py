@@ -13,6 +13,7 @@ from mmlearn_b200 import ContrastiveLoss, LossPairSpec
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+nosync = len(sys.argv) > 4 and sys.argv[4] == "nosync"  # let the host run ahead between steps
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -45,7 +46,9 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(steps):
         step()
-        torch.cuda.synchronize()
+        if not nosync:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
 if rank != 0:
     if world > 1:
         dist.barrier()
