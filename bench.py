@@ -144,6 +144,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout; this program's stdout is the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     warmup = max(args.warmup, 3)
@@ -307,6 +309,22 @@ def main():
                "sample": f"one rank's share: {args.cpu_rows} query rows x all {N} keys, both "
                          f"directions, fwd+bwd, 3 steps, torch CPU fp32 ({r['ms_per_step']:.0f} ms/step)"}
 
+    # ---- (5) the library baseline on the same GPU: the reference's torch ops (cuBLAS + ATen) -----
+    lib_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_reference import time_rank_share
+
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            r = time_rank_share(N, d, N, steps=5, warmup=2, device=str(dev), autocast_bf16=True)
+            lib_gpu = {"value": r["samples_per_s"], "unit": "samples/s", "ms_per_step": r["ms_per_step"],
+                       "kind": "port of the reference's torch ops on cuda:0 under bf16 autocast "
+                               "(cuBLAS GEMMs + ATen cross_entropy; logits materialised in HBM); "
+                               "id matching excluded (the reference's needs a 2.1 GB N x N temporary)"}
+        except Exception as exc:  # noqa: BLE001 - a baseline must never break the bench line
+            lib_gpu = {"value": None, "error": str(exc)[:200]}
+
     if rank == 0:
         line = {
             "metric": "contrastive loss fwd+bwd samples/sec @B=32k,d=512",
@@ -325,6 +343,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "torch_gpu_baseline": lib_gpu,
             "loss": loss_value,
         }
         print(json.dumps(line))

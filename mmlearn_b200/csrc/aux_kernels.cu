@@ -204,7 +204,9 @@ __device__ __forceinline__ void store8(void* base, long long elem, const float (
 
 // kDirect: idx == identity and this is the only contribution to the rows -> plain stores in the
 // output dtype ODT; otherwise fp32 atomics into `grad` (ODT == 0).
-template <int DT, int ODT, bool kDirect>
+// MAXV = ceil(d / 256) register-resident 8-wide column groups per lane (dispatch below): sizing the
+// arrays to the actual d keeps the register count low enough for full occupancy at d = 512.
+template <int DT, int ODT, bool kDirect, int MAXV>
 __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
                                    const __nv_bfloat16* __restrict__ partner,
                                    const float* __restrict__ partner_inv, long long n, int d,
@@ -217,7 +219,6 @@ __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
   if (row >= n) return;
   const float coef = weight * (gout ? *gout : 1.f) * (*scale);
   const long long srow = idx ? idx[row] : row;
-  constexpr int MAXV = 8;  // supports d <= 2048 with the register-resident path
   float g[MAXV][8];
   float x[MAXV][8];
   float dot = 0.f;
@@ -328,10 +329,19 @@ cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16,
   const int wpb = 4;
   const unsigned blocks = unsigned((n + wpb - 1) / wpb);
   auto* pb = static_cast<const __nv_bfloat16*>(partner_bf16);
-#define MMCL_UNPACK(DT, ODT, DIRECT)                                                              \
-  unpack_grad_kernel<DT, ODT, DIRECT><<<blocks, wpb * 32, 0, stream>>>(                           \
+  const int nv = int((d + 255) / 256);  // d <= 2048 -> 1..8
+#define MMCL_UNPACK_NV(DT, ODT, DIRECT, NV)                                                       \
+  unpack_grad_kernel<DT, ODT, DIRECT, NV><<<blocks, wpb * 32, 0, stream>>>(                       \
       dacc, pb, partner_inv, n, int(d), (float)weight, (float)pos_coef, gout, scale, src,         \
       inv_norm, normalize, idx, grad)
+#define MMCL_UNPACK(DT, ODT, DIRECT)                                                              \
+  do {                                                                                            \
+    if (nv <= 1) MMCL_UNPACK_NV(DT, ODT, DIRECT, 1);                                              \
+    else if (nv == 2) MMCL_UNPACK_NV(DT, ODT, DIRECT, 2);                                         \
+    else if (nv == 3) MMCL_UNPACK_NV(DT, ODT, DIRECT, 3);                                         \
+    else if (nv == 4) MMCL_UNPACK_NV(DT, ODT, DIRECT, 4);                                         \
+    else MMCL_UNPACK_NV(DT, ODT, DIRECT, 8);                                                      \
+  } while (0)
 #define MMCL_UNPACK_SRC(ODT, DIRECT)                                                              \
   do {                                                                                            \
     if (src_dtype == 0) MMCL_UNPACK(0, ODT, DIRECT);                                              \
@@ -349,6 +359,7 @@ cudaError_t launch_unpack_grad(const float* dacc, const void* partner_bf16,
   }
 #undef MMCL_UNPACK_SRC
 #undef MMCL_UNPACK
+#undef MMCL_UNPACK_NV
   count_launches(1);
   return cudaGetLastError();
 }

@@ -30,6 +30,7 @@ from torch import nn
 
 from . import _lib
 from ._lib import MmclError, check, counts_array, ptr
+from .alignment import modality_alignment_loss
 from .modalities import LossPairSpec, Modalities
 from .plan import PairPlan, all_gather_ints, dist_info
 from .steady import SteadyPlan, table_rows
@@ -868,7 +869,7 @@ class ContrastiveLoss(nn.Module):
     gather_with_grad : bool, optional, default=False
         Whether to gather tensors with gradients.
     modality_alignment : bool, optional, default=False
-        Whether to include the modality alignment loss (not part of the fused path; raises).
+        Whether to include the modality alignment loss (dense torch branch, see alignment.py).
     cache_labels : bool, optional, default=False
         Whether to cache the labels.
     """
@@ -921,10 +922,6 @@ class ContrastiveLoss(nn.Module):
         modality_loss_pairs: list[LossPairSpec],
     ) -> torch.Tensor:
         """Calculate the contrastive loss (same contract as contrastive.py:59-85)."""
-        if self.modality_alignment:
-            raise NotImplementedError(
-                "modality_alignment=True is outside the fused hot path (SURVEY.md section 8, row "
-                "a11); use the reference module for that term.")
         if not embeddings:
             raise ValueError("embeddings is empty")
         keys = list(embeddings.keys())
@@ -950,6 +947,11 @@ class ContrastiveLoss(nn.Module):
         loss = _FusedContrastiveFn.apply(run, logit_scale, *embs)
         if not run.need_grad:
             run.release()  # nothing will be back-propagated: free the arena buffer for reuse
+        if self.modality_alignment:
+            # contrastive.py:146-149; a dense torch branch outside the fused path (alignment.py)
+            align = modality_alignment_loss(embeddings, logit_scale, self.l2_normalize,
+                                            self.local_loss, self.gather_with_grad)
+            return loss + align if run.losses_present else align
         if not run.losses_present:
             # no loss to compute (e.g. no paired data in batch): contrastive.py:151-158
             return torch.zeros((), device=logit_scale.device, dtype=embs[0].dtype)

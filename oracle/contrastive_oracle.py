@@ -94,6 +94,32 @@ class OracleResult:
     matched: list  # per rank: list (per pair) of (idx_a, idx_b) local index arrays
 
 
+def modality_alignment_oracle(all_embeddings: dict, logit_scale) -> torch.Tensor:
+    """Literal restatement of ``_compute_modality_alignment_loss`` (contrastive.py:344-413),
+    Python ``itertools.combinations`` loop and block-offset rule included."""
+    import itertools
+
+    keys = list(all_embeddings.keys())
+    feats = torch.cat(list(all_embeddings.values()), dim=0)  # :374
+    pos = []
+    for idx, k in enumerate(all_embeddings):  # :376-386
+        off = 0 if idx == 0 else all_embeddings[keys[idx - 1]].size(0)
+        for i, j in itertools.combinations(range(all_embeddings[k].size(0)), 2):
+            pos.append((i + off, j + off))
+    logits = logit_scale * (feats @ feats.T)  # :387
+    target = torch.eye(feats.size(0), dtype=logits.dtype)  # :389
+    if pos:
+        pi = torch.tensor(pos)
+        target[pi[:, 0], pi[:, 1]] = 1  # :390
+    bce = F.binary_cross_entropy_with_logits(logits, target, reduction="none")  # :392-394
+    tp = target.bool()
+    loss_pos = torch.where(tp, bce, torch.zeros_like(bce)).sum(dim=1)  # :401-409
+    loss_neg = torch.where(~tp, bce, torch.zeros_like(bce)).sum(dim=1)
+    num_pos = target.sum(dim=1)  # :410
+    num_neg = logits.size(0) - num_pos  # :411
+    return ((loss_pos / num_pos) + (loss_neg / num_neg)).mean()  # :413
+
+
 def contrastive_oracle(
     emb_per_rank: Sequence[dict],
     ids_per_rank: Sequence[dict],
@@ -106,6 +132,7 @@ def contrastive_oracle(
     dtype: torch.dtype = torch.float32,
     want_grads: bool = True,
     fast_match: bool = False,
+    modality_alignment: bool = False,
 ) -> OracleResult:
     """Restates ``ContrastiveLoss.forward`` (contrastive.py:59-160) for W = len(emb_per_rank).
 
@@ -245,6 +272,8 @@ def contrastive_oracle(
                         gross[rank] += float(
                             (g.abs() * lg.abs()).sum() * abs(pair.weight) / (2 * lt.numel())
                             / abs(float(s)))
+        if modality_alignment:  # contrastive.py:146-149
+            rank_losses.append(modality_alignment_oracle(all_emb, scales[rank]))
         if not rank_losses:
             rank_losses.append(torch.zeros((), dtype=dtype))  # contrastive.py:151-158
         losses_t.append(torch.stack(rank_losses).sum())

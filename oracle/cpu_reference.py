@@ -20,10 +20,11 @@ import torch.nn.functional as F
 def rank_share_step(a_all: torch.Tensor, b_all: torch.Tensor, b: int, scale: float):
     """fwd+bwd of rank 0's loss over its first ``b`` rows against all N gathered keys.
 
-    ``a_all``/``b_all``: fp32 [N, d] raw embeddings (bf16-representable values)."""
+    ``a_all``/``b_all``: fp32 [N, d] raw embeddings (bf16-representable values), on the CPU or
+    (``time_rank_share(device="cuda")``: the same torch ops through cuBLAS / ATen) on a GPU."""
     a_loc = a_all[:b].clone().requires_grad_(True)
     b_loc = b_all[:b].clone().requires_grad_(True)
-    s = torch.tensor(scale, requires_grad=True)
+    s = torch.tensor(scale, requires_grad=True, device=a_all.device)
     # contrastive.py:89-90 (every rank normalises its own rows; the gathered rows arrive normalised)
     fa = F.normalize(a_loc, p=2, dim=-1)
     fb = F.normalize(b_loc, p=2, dim=-1)
@@ -36,26 +37,41 @@ def rank_share_step(a_all: torch.Tensor, b_all: torch.Tensor, b: int, scale: flo
     # contrastive.py:327-332
     logits_a = s * (fa @ all_b.T)
     logits_b = s * (fb @ all_a.T)
-    labels = torch.arange(b)  # contrastive.py:194-212 with off_0 = 0
+    labels = torch.arange(b, device=a_all.device)  # contrastive.py:194-212 with off_0 = 0
     loss = (F.cross_entropy(logits_a, labels) + F.cross_entropy(logits_b, labels)) / 2
     loss.backward()
     return float(loss), a_loc.grad, b_loc.grad, float(s.grad)
 
 
 def time_rank_share(n: int, d: int, b: int, steps: int, warmup: int, seed: int = 1234,
-                    threads: int | None = None):
-    """Median-free simple timing: total wall time of ``steps`` steps -> samples/s = b*steps/t."""
+                    threads: int | None = None, device: str = "cpu", autocast_bf16: bool = False):
+    """Median-free simple timing: total wall time of ``steps`` steps -> samples/s = b*steps/t.
+
+    ``device="cuda"`` times the same restatement through torch's CUDA kernels (cuBLAS + ATen),
+    optionally under bf16 autocast as Lightning's ``bf16-mixed`` would run the reference
+    (mmlearn/cli/run.py:46-49): the library baseline on the same GPU."""
     if threads:
         torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(n, d, generator=g).to(torch.bfloat16).float()
     g = torch.Generator().manual_seed(seed + 1)
     bb = (0.5 * a + torch.randn(n, d, generator=g)).to(torch.bfloat16).float()
+    a, bb = a.to(device), bb.to(device)
+    cuda = a.is_cuda
+
+    def one():
+        if cuda and autocast_bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return rank_share_step(a, bb, b, 1 / 0.07)
+        return rank_share_step(a, bb, b, 1 / 0.07)
+
     for _ in range(warmup):
-        rank_share_step(a, bb, b, 1 / 0.07)
+        one()
+    if cuda:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        rank_share_step(a, bb, b, 1 / 0.07)
+        one()  # float(loss) inside synchronises the device every step
     dt = time.perf_counter() - t0
     return dict(seconds=dt, ms_per_step=1e3 * dt / steps, samples_per_s=b * steps / dt,
                 threads=torch.get_num_threads())

@@ -106,6 +106,38 @@ def build_cases():
     cases["w2_rank1_unpaired"] = dict(
         world=2, emb=embs, ids=idss, scale=1 / 0.07, pairs=[("rgb", "text", 1.0)],
         flags=dict(l2_normalize=True, local_loss=True, gather_with_grad=False, cache_labels=False))
+    # 7. modality_alignment term (contrastive.py:344-413).  Unequal modality sizes in the
+    # three-modality case exercise the reference's block-offset rule.
+    n, d = 12, 32
+    a = emb(n, d)
+    b = emb(n, d, a)
+    idn = _ids(np.zeros(n), np.arange(n))
+    cases["w1_align_two_mods"] = dict(
+        world=1, emb=[{"rgb": a, "text": b}], ids=[{"rgb": idn, "text": idn}], scale=10.0,
+        pairs=[("rgb", "text", 1.0)],
+        flags=dict(l2_normalize=True, local_loss=False, gather_with_grad=False, cache_labels=False,
+                   modality_alignment=True))
+    c = emb(5, d, a[:5])
+    cases["w1_align_three_mods"] = dict(
+        world=1, emb=[{"rgb": a[:10], "text": b[:7], "audio": c}],
+        ids=[{"rgb": idn[:10], "text": idn[:7], "audio": idn[:5]}], scale=5.0,
+        pairs=[("rgb", "text", 1.0), ("text", "audio", 0.5)],
+        flags=dict(l2_normalize=True, local_loss=False, gather_with_grad=False, cache_labels=False,
+                   modality_alignment=True))
+    n, W = 16, 2
+    a = emb(n, d)
+    b = emb(n, d, a)
+    for gg in (True, False):
+        embs, idss = [], []
+        for r in range(W):
+            sl = slice(r * n // W, (r + 1) * n // W)
+            idr = _ids(np.zeros(n // W), np.arange(n)[sl])
+            embs.append({"rgb": a[sl], "text": b[sl]})
+            idss.append({"rgb": idr, "text": idr})
+        cases[f"w2_align_ll0_gg{int(gg)}"] = dict(
+            world=W, emb=embs, ids=idss, scale=8.0, pairs=[("rgb", "text", 1.0)],
+            flags=dict(l2_normalize=True, local_loss=False, gather_with_grad=gg,
+                       cache_labels=False, modality_alignment=True))
     return cases
 
 
@@ -117,7 +149,7 @@ def _run_rank(rank, world, case, init_file, ret):
     torch.manual_seed(0)
     Loss = ref["contrastive"].ContrastiveLoss
     Pair = ref["task_stub"].LossPairSpec
-    loss_fn = Loss(modality_alignment=False, **case["flags"])
+    loss_fn = Loss(**{"modality_alignment": False, **case["flags"]})
     leaves = {f"{m}_embedding": torch.tensor(v, requires_grad=True)
               for m, v in case["emb"][rank].items()}
     ids = {m: torch.from_numpy(v) for m, v in case["ids"][rank].items()}
@@ -155,7 +187,10 @@ def run_case(case):
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
     for name, case in build_cases().items():
+        if only and not any(name.startswith(p) for p in only):
+            continue  # keep the committed fixtures of the other cases untouched
         ret = run_case(case)
         flat = {"world": np.int64(case["world"]), "scale": np.float64(case["scale"]),
                 "pairs": np.array([f"{p[0]}|{p[1]}|{p[2]!r}" for p in case["pairs"]]),
@@ -169,6 +204,8 @@ def main():
                 flat[f"r{r}_out_{k}"] = v
         np.savez_compressed(os.path.join(OUT, f"loss_{name}.npz"), **flat)
         print(name, [float(ret[r]["loss"]) for r in range(case["world"])])
+    if only:
+        return
     # find_matching_indices: the reference function on seeded random ids (duplicates, misses)
     fmi = ref["example"].find_matching_indices
     rng = np.random.RandomState(3)

@@ -18,7 +18,7 @@ DEV = "cuda:0"
 def _run_fused(emb, ids, scale, pairs, flags, dtype=torch.float32, scale_vec=None):
     from mmlearn_b200 import ContrastiveLoss, LossPairSpec
 
-    fn = ContrastiveLoss(modality_alignment=False, **flags)
+    fn = ContrastiveLoss(**{"modality_alignment": False, **flags})
     leaves = {f"{m}_embedding": torch.as_tensor(v).to(DEV).to(dtype).requires_grad_(True)
               for m, v in emb.items()}
     idt = {m: torch.as_tensor(v).to(DEV) for m, v in ids.items()}

@@ -26,7 +26,7 @@ def _worker(rank, world, name, init_file, ret, no_symm=False):
     from mmlearn_b200 import ContrastiveLoss, LossPairSpec
 
     case = load_case(name)
-    fn = ContrastiveLoss(modality_alignment=False, **case["flags"])
+    fn = ContrastiveLoss(**{"modality_alignment": False, **case["flags"]})
     leaves = {f"{m}_embedding": torch.from_numpy(v).to(dev).requires_grad_(True)
               for m, v in case["emb"][rank].items()}
     ids = {m: torch.from_numpy(v).to(dev) for m, v in case["ids"][rank].items()}
@@ -85,7 +85,7 @@ def _worker_sequence(rank, world, names, init_file, ret):
     from mmlearn_b200 import ContrastiveLoss, LossPairSpec
 
     flags = load_case(names[0])["flags"]
-    fn = ContrastiveLoss(modality_alignment=False, **flags)
+    fn = ContrastiveLoss(**{"modality_alignment": False, **flags})
     outs = []
     for name in names:
         case = load_case(name)
