@@ -155,6 +155,27 @@ int mmcl_sim_lse_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void*
                      const float* kinv, float* lse, float* esum, void* workspace,
                      size_t workspace_bytes, mmcl_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Retrieval rank on the same tcgen05 mainloop.
+ *   mmcl_indexed_similarity: out[i] = qinv_i * kinv_t * (q_i . k_t) + add,  t = index[i]
+ *                            (fp32 accumulation; index out of range -> `add`)
+ *   mmcl_sim_rank_fwd:       rank[i] = #{ j != skip[i] : qinv_i * kinv_j * (q_i . k_j) > thr[i] }
+ *                            (skip may be NULL)
+ * With thr = similarity of the positive (+ a tie margin) and skip = index, rank[i] is the number of database
+ * items that beat query i's positive; recall@k for every k is mean(rank < k).  The nq x nk
+ * similarity matrix only exists as tiles in tensor memory: no matrix, no top-k, no sort.
+ * Replaces: _safe_matmul + torch.topk + gather in RetrievalRecallAtK._process_batch /
+ * _recall_at_k (mmlearn/modules/metrics/retrieval_recall.py:232-275), which the reference runs
+ * on the CPU in a thread pool.  Workspace: mmcl_sim_lse_workspace_bytes(nq, nk, d).
+ * ------------------------------------------------------------------------------------------ */
+int mmcl_indexed_similarity(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                            int64_t nk, int64_t d, const int64_t* index, const float* qinv,
+                            const float* kinv, double add, float* out, mmcl_stream stream);
+int mmcl_sim_rank_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                      int64_t nk, int64_t d, const float* qinv, const float* kinv,
+                      const float* thr, const int64_t* skip, int64_t* rank, void* workspace,
+                      size_t workspace_bytes, mmcl_stream stream);
+
 /* pos[i] = S_{i, label_offset + i}  (the positive logit; labels are off_r + i,
  * contrastive.py:194-212).  fp32 accumulation over the same bf16 rows the GEMM reads. */
 int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,

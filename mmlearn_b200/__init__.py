@@ -6,6 +6,8 @@ Public surface (mirrors the reference for this path only):
   ``mmlearn.modules.losses.ContrastiveLoss``
 * :class:`LossPairSpec`, :data:`Modalities` -- interface mirrors
 * :func:`find_matching_indices` -- device version of the reference function
+* :class:`RetrievalRecallAtK` -- drop-in for ``mmlearn.modules.metrics.RetrievalRecallAtK`` on the
+  same similarity mainloop
 
 Everything computes through ``libmmcl.so`` (``include/mmcl.h``); there is no CPU fallback.
 """
@@ -14,6 +16,7 @@ from . import _lib
 from .loss import ContrastiveLoss, FusedContrastiveLoss, find_matching_indices, get_handle
 from .modalities import LossPairSpec, Modalities
 from .plan import PairPlan
+from .retrieval import RetrievalRecallAtK
 
 __all__ = [
     "ContrastiveLoss",
@@ -21,6 +24,7 @@ __all__ = [
     "LossPairSpec",
     "Modalities",
     "PairPlan",
+    "RetrievalRecallAtK",
     "find_matching_indices",
     "get_handle",
 ]

@@ -73,6 +73,12 @@ SYMBOLS = {
                                  c_void_p]),
     "mmcl_positive_logits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                      c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmcl_indexed_similarity": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                        c_void_p, c_void_p, c_void_p, c_double, c_void_p,
+                                        c_void_p]),
+    "mmcl_sim_rank_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "mmcl_pair_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "mmcl_sim_grad_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,

@@ -365,6 +365,43 @@ int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const v
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_positive_logits");
 }
 
+int mmcl_indexed_similarity(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                            int64_t nk, int64_t d, const int64_t* index, const float* qinv,
+                            const float* kinv, double add, float* out, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_indexed_similarity: null handle");
+  int rc = check_sim_args("mmcl_indexed_similarity", q_bf16, nq, k_bf16, nk, d);
+  if (rc) return rc;
+  REQUIRE(nq == 0 || (out && index), "mmcl_indexed_similarity: null index/out");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_indexed_similarity(q_bf16, nq, k_bf16, nk, d, index, qinv, kinv,
+                                            float(add), out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_indexed_similarity");
+}
+
+int mmcl_sim_rank_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                      int64_t nk, int64_t d, const float* qinv, const float* kinv,
+                      const float* thr, const int64_t* skip, int64_t* rank, void* workspace,
+                      size_t workspace_bytes, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_sim_rank_fwd: null handle");
+  int rc = check_sim_args("mmcl_sim_rank_fwd", q_bf16, nq, k_bf16, nk, d);
+  if (rc) return rc;
+  if (nq == 0) return MMCL_OK;
+  REQUIRE(nk > 0, "mmcl_sim_rank_fwd: nk must be positive");
+  REQUIRE(thr && rank, "mmcl_sim_rank_fwd: null thr/rank");
+  if (workspace_bytes < sim_lse_workspace_bytes(h->num_sms, nq, nk, d) || !workspace)
+    return fail(MMCL_ERR_WORKSPACE, "mmcl_sim_rank_fwd: workspace too small");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const char* err = nullptr;
+  cudaError_t e = launch_sim_rank_fwd(h->num_sms, q_bf16, nq, k_bf16, nk, d, qinv, kinv, thr,
+                                      reinterpret_cast<const long long*>(skip),
+                                      reinterpret_cast<long long*>(rank), workspace,
+                                      workspace_bytes, static_cast<cudaStream_t>(stream), &err);
+  if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_rank_fwd");
+  return MMCL_OK;
+}
+
 int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const float* esum_a,
                    const float* esum_b, const float* pos, int64_t n, double weight, double n_norm,
                    const float* scale, float* out2, mmcl_stream stream) {

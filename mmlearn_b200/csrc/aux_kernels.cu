@@ -92,11 +92,12 @@ __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long
                                        const __nv_bfloat16* __restrict__ k, long long nk, int d,
                                        long long label_offset, const float* __restrict__ scale,
                                        const float* __restrict__ qinv,
-                                       const float* __restrict__ kinv, float* __restrict__ pos) {
+                                       const float* __restrict__ kinv, float* __restrict__ pos,
+                                       const int64_t* __restrict__ index, float add) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nq) return;
-  const long long krow = label_offset + row;
+  const long long krow = index ? index[row] : label_offset + row;
   float acc = 0.f;
   if (krow >= 0 && krow < nk) {
     for (int c = lane * 8; c < d; c += 256) {
@@ -109,10 +110,10 @@ __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long
   }
   acc = warp_sum(acc);
   if (lane == 0) {
-    float f = *scale;
+    float f = scale ? *scale : 1.f;
     if (qinv) f *= qinv[row];
     if (kinv && krow >= 0 && krow < nk) f *= kinv[krow];
-    pos[row] = acc * f;
+    pos[row] = acc * f + add;
   }
 }
 
@@ -295,7 +296,20 @@ cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, l
   const int wpb = 8;
   positive_logits_kernel<<<unsigned((nq + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(q), nq, static_cast<const __nv_bfloat16*>(k), nk, int(d),
-      label_offset, scale, qinv, kinv, pos);
+      label_offset, scale, qinv, kinv, pos, nullptr, 0.f);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_indexed_similarity(const void* q, long long nq, const void* k, long long nk,
+                                      long long d, const int64_t* index, const float* qinv,
+                                      const float* kinv, float add, float* out,
+                                      cudaStream_t stream) {
+  if (nq == 0) return cudaSuccess;
+  const int wpb = 8;
+  positive_logits_kernel<<<unsigned((nq + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(q), nq, static_cast<const __nv_bfloat16*>(k), nk, int(d), 0,
+      nullptr, qinv, kinv, out, index, add);
   count_launches(1);
   return cudaGetLastError();
 }

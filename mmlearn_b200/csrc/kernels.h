@@ -19,6 +19,12 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
                                const float* kinv, float* lse, float* esum, void* workspace,
                                size_t workspace_bytes, cudaStream_t stream, const char** err);
 
+cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const void* k,
+                                long long nk, long long d, const float* qinv, const float* kinv,
+                                const float* thr, const long long* tgt, long long* rank,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                                const char** err);
+
 // sim_bwd.cu
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
                                 long long ny, long long d, const float* scale, const float* xinv,
@@ -42,6 +48,10 @@ cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, l
                                    long long d, long long label_offset, const float* scale,
                                    const float* qinv, const float* kinv, float* pos,
                                    cudaStream_t stream);
+cudaError_t launch_indexed_similarity(const void* q, long long nq, const void* k, long long nk,
+                                      long long d, const int64_t* index, const float* qinv,
+                                      const float* kinv, float add, float* out,
+                                      cudaStream_t stream);
 cudaError_t launch_pair_loss(const float* lse_a, const float* lse_b, const float* esum_a,
                              const float* esum_b, const float* pos, long long n, double weight,
                              double n_norm, const float* scale, float* out2, cudaStream_t stream);

@@ -41,9 +41,14 @@ struct FwdParams {
   float* part_m;
   float* part_l;
   float* part_t;
+  const float* thr;  // rank mode: per-row threshold on  qinv_i * kinv_j * (q_i . k_j)
+  const long long* tgt;  // rank mode: per-row key index that is never counted (the positive) or null
 };
 
-template <bool kQRes>
+// kRank == false: online log-sum-exp epilogue (the loss).  kRank == true: the same mainloop with a
+// counting epilogue -- per row, the number of keys whose similarity exceeds the row's threshold
+// (retrieval rank of the positive, mmcl_sim_rank_fwd); one multiply + compare per logit, no MUFU.
+template <bool kQRes, bool kRank>
 __global__ void __launch_bounds__(256, 1)
 sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const FwdParams p) {
@@ -167,7 +172,7 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int q = warp - 4;  // == warp % 4: TMEM lane quadrant
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
-    const float s = *p.scale;
+    const float s = kRank ? 1.f : *p.scale;
     const bool neg = s < 0.f;
     uint32_t acc = 0;
     for (long long t = t_begin; t < t_end;) {
@@ -175,8 +180,47 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       int kt1 = kt0 + int(t_end - t);
       if (kt1 > p.nkt) kt1 = p.nkt;
       float m = -INFINITY, l = 0.f, tt = 0.f;
-      // logit = s * (q_i.k_j) * qinv_i * kinv_j ; c folds everything that depends on the row
       const int grow = qt * BM + row;
+      if (kRank) {
+        // count_j [ qinv_i * kinv_j * (q_i . k_j) > thr_i ]  ==  [ x_ij * kinv_j > thr_i / qinv_i ]
+        const float qi = (p.qinv && grow < p.nq) ? p.qinv[grow] : 1.f;
+        const float th = (grow < p.nq ? p.thr[grow] : INFINITY) / qi;
+        const long long tg = (p.tgt && grow < p.nq) ? p.tgt[grow] : -1;
+        int cnt = 0;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
+          float* kv = sKinv + ab * BN;
+          for (int j = et; j < BN; j += 128) {
+            const int gk = kt * BN + j;
+            kv[j] = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+          }
+          named_bar_sync(1, 128);
+          mbar_wait(&acc_full[ab], aphase);
+          tc_fence_after();
+          const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
+          const int valid = p.nk - kt * BN;
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            if (ch == BN / 32 - 1) {
+              tc_fence_before();
+              mbar_arrive(&acc_empty[ab]);
+            }
+            const int cv = valid - ch * 32;
+            const float* kc = kv + ch * 32;
+            const long long tl = tg - ((long long)kt * BN + ch * 32);  // the positive's slot, if here
+            const int tloc = (tl >= 0 && tl < 32) ? int(tl) : -1;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              cnt += (e < cv && e != tloc && __uint_as_float(v[e]) * kc[e] > th) ? 1 : 0;
+          }
+          ++acc;
+        }
+        m = float(cnt);  // exact below 2^24 keys per segment
+      } else {
+      // logit = s * (q_i.k_j) * qinv_i * kinv_j ; c folds everything that depends on the row
       const float c = s * LOG2E * ((p.qinv && grow < p.nq) ? p.qinv[grow] : 1.f);
       for (int kt = kt0; kt < kt1; ++kt) {
         const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
@@ -258,6 +302,7 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         ++acc;
       }
+      }
       // partial statistics of this (q-tile, key range) segment
       const long long first_tile = (long long)qt * p.nkt;
       const int c_first = int(first_tile / p.tiles_per_cta);
@@ -297,6 +342,20 @@ __global__ void lse_combine_kernel(FwdParams p, float* __restrict__ lse, float* 
   if (esum) esum[row] = sc * T / L;
 }
 
+// Rank mode: total count of each row over the key segments of different CTAs.
+__global__ void rank_combine_kernel(FwdParams p, long long* __restrict__ rank) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.nq) return;
+  const int qt = row / BM;
+  const long long first_tile = (long long)qt * p.nkt;
+  const int c_first = int(first_tile / p.tiles_per_cta);
+  const int c_last = int((first_tile + p.nkt - 1) / p.tiles_per_cta);
+  long long total = 0;
+  for (int s = 0; s <= c_last - c_first; ++s)
+    total += (long long)p.part_m[(long long)s * p.part_stride + row];
+  rank[row] = total;
+}
+
 int fwd_plan(int num_sms, long long nq, long long nk, long long d, FwdParams* p, bool* qres,
              size_t* smem_bytes) {
   p->nq = int(nq);
@@ -330,6 +389,35 @@ size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long lon
   return size_t(3) * p.max_slots * p.part_stride * sizeof(float);
 }
 
+namespace {
+
+template <bool kRank>
+cudaError_t launch_fwd(int num_sms, const void* q, long long nq, const void* k, long long nk,
+                       long long d, FwdParams p, bool qres, size_t smem, cudaStream_t stream,
+                       const char** err) {
+  CUtensorMap tmQ, tmK;
+  if (make_tmap_bf16_sw128(&tmQ, q, nq, d, d, BM) || make_tmap_bf16_sw128(&tmK, k, nk, d, d, BN)) {
+    *err = "sim_fwd: cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  const int ctas = int((p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
+  cudaError_t e;
+  if (qres) {
+    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true, kRank>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    sim_lse_fwd_kernel<true, kRank><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
+  } else {
+    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false, kRank>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    sim_lse_fwd_kernel<false, kRank><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
 cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const void* k,
                                long long nk, long long d, const float* scale, const float* qinv,
                                const float* kinv, float* lse, float* esum, void* workspace,
@@ -346,30 +434,43 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
   p.scale = scale;
   p.qinv = qinv;
   p.kinv = kinv;
+  p.thr = nullptr;
+  p.tgt = nullptr;
   p.part_m = static_cast<float*>(workspace);
   p.part_l = p.part_m + size_t(p.max_slots) * p.part_stride;
   p.part_t = p.part_l + size_t(p.max_slots) * p.part_stride;
-  CUtensorMap tmQ, tmK;
-  if (make_tmap_bf16_sw128(&tmQ, q, nq, d, d, BM) || make_tmap_bf16_sw128(&tmK, k, nk, d, d, BN)) {
-    *err = "sim_lse_fwd: cuTensorMapEncodeTiled failed";
-    return cudaErrorInvalidValue;
-  }
-  const int ctas = int((p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
-  cudaError_t e;
-  if (qres) {
-    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(smem));
-    if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<true><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
-  } else {
-    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<false><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
-  }
-  e = cudaGetLastError();
+  cudaError_t e = launch_fwd<false>(num_sms, q, nq, k, nk, d, p, qres, smem, stream, err);
   if (e != cudaSuccess) return e;
   lse_combine_kernel<<<(p.nq + 255) / 256, 256, 0, stream>>>(p, lse, esum);
+  count_launches(2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const void* k,
+                                long long nk, long long d, const float* qinv, const float* kinv,
+                                const float* thr, const long long* tgt, long long* rank,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                                const char** err) {
+  FwdParams p;
+  bool qres;
+  size_t smem;
+  fwd_plan(num_sms, nq, nk, d, &p, &qres, &smem);
+  const size_t need = size_t(3) * p.max_slots * p.part_stride * sizeof(float);
+  if (workspace_bytes < need) {
+    *err = "sim_rank_fwd: workspace too small";
+    return cudaErrorInvalidValue;
+  }
+  p.scale = nullptr;
+  p.qinv = qinv;
+  p.kinv = kinv;
+  p.thr = thr;
+  p.tgt = tgt;
+  p.part_m = static_cast<float*>(workspace);
+  p.part_l = p.part_m + size_t(p.max_slots) * p.part_stride;
+  p.part_t = p.part_l + size_t(p.max_slots) * p.part_stride;
+  cudaError_t e = launch_fwd<true>(num_sms, q, nq, k, nk, d, p, qres, smem, stream, err);
+  if (e != cudaSuccess) return e;
+  rank_combine_kernel<<<(p.nq + 255) / 256, 256, 0, stream>>>(p, rank);
   count_launches(2);
   return cudaGetLastError();
 }

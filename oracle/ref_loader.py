@@ -130,3 +130,84 @@ def load_reference() -> dict[str, types.ModuleType]:
         contrastive=contrastive, example=example, modalities=modalities, task_stub=cp
     )
     return _CACHE
+
+
+def load_reference_retrieval() -> types.ModuleType:
+    """The unmodified ``mmlearn/modules/metrics/retrieval_recall.py`` under import stubs.
+
+    torchmetrics is not installable here, so the pieces the file imports are restated from
+    torchmetrics 1.6.2 (pinned in the reference's ``uv.lock``): a minimal ``Metric`` base
+    (``add_state``, ``reset``, single-process ``distributed_available_fn``), ``dim_zero_cat``,
+    ``_check_same_shape``, ``_retrieval_aggregate``, ``_safe_matmul``.  Everything that decides the
+    metric's value -- ``update``, ``compute``, ``_process_batch``, ``_recall_at_k`` -- is the
+    reference's own code."""
+    if "retrieval" in _CACHE:
+        return _CACHE["retrieval"]
+    load_reference()
+    import torch
+
+    tm = sys.modules["torchmetrics"]
+
+    class Metric(torch.nn.Module):
+        def __init__(self, **kwargs):
+            super().__init__()
+            self._defaults = {}
+            self.distributed_available_fn = lambda: False
+            self.process_group = None
+
+        def add_state(self, name, default, dist_reduce_fx=None):
+            self._defaults[name] = default
+            setattr(self, name, [] if isinstance(default, list) else default.clone())
+
+        def reset(self):
+            for name, default in self._defaults.items():
+                setattr(self, name, [] if isinstance(default, list) else default.clone())
+
+    tm.Metric = Metric
+
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+
+    base = mod("torchmetrics.retrieval.base")
+    mod("torchmetrics.retrieval").base = base
+
+    def _retrieval_aggregate(values, aggregation="mean", dim=None):
+        if aggregation == "mean":
+            return values.mean() if dim is None else values.mean(dim=dim)
+        if aggregation == "median":
+            return values.median() if dim is None else values.median(dim=dim).values
+        if aggregation == "min":
+            return values.min() if dim is None else values.min(dim=dim).values
+        if aggregation == "max":
+            return values.max() if dim is None else values.max(dim=dim).values
+        return aggregation(values, dim=dim)
+
+    base._retrieval_aggregate = _retrieval_aggregate
+    checks = mod("torchmetrics.utilities.checks")
+
+    def _check_same_shape(preds, target):
+        if preds.shape != target.shape:
+            raise RuntimeError(
+                "Predictions and targets are expected to have the same shape, "
+                f"but got {preds.shape} and {target.shape}.")
+
+    checks._check_same_shape = _check_same_shape
+    data = mod("torchmetrics.utilities.data")
+
+    def dim_zero_cat(x):
+        if isinstance(x, torch.Tensor):
+            return x
+        x = [y.unsqueeze(0) if y.numel() == 1 and y.ndim == 0 else y for y in x]
+        if not x:
+            raise ValueError("No samples to concatenate")
+        return torch.cat(x, dim=0)
+
+    data.dim_zero_cat = dim_zero_cat
+    distm = mod("torchmetrics.utilities.distributed")
+    distm.gather_all_tensors = lambda t, group=None: [t]
+    sys.modules["mmlearn.modules.metrics"] = types.ModuleType("mmlearn.modules.metrics")
+    _CACHE["retrieval"] = _load("mmlearn.modules.metrics.retrieval_recall",
+                                "mmlearn/modules/metrics/retrieval_recall.py")
+    return _CACHE["retrieval"]
