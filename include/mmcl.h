@@ -176,6 +176,13 @@ int mmcl_sim_rank_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void
                       const float* thr, const int64_t* skip, int64_t* rank, void* workspace,
                       size_t workspace_bytes, mmcl_stream stream);
 
+/* Caller glue of the task: log_scale[i] <- clamp(log_scale[i], 0,
+ * log(max_scale)) IN PLACE and scale_out[i] = exp(log_scale[i]), one launch.
+ * Replaces: `self.log_logit_scale.clamp_(0, math.log(self.max_logit_scale))` followed by
+ * `self.log_logit_scale.exp()` (mmlearn/tasks/contrastive_pretraining.py:488-489, 610). */
+int mmcl_logit_scale(mmcl_handle* h, float* log_scale, int64_t n, double max_scale,
+                     float* scale_out, mmcl_stream stream);
+
 /* pos[i] = S_{i, label_offset + i}  (the positive logit; labels are off_r + i,
  * contrastive.py:194-212).  fp32 accumulation over the same bf16 rows the GEMM reads. */
 int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,

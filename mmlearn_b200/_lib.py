@@ -73,6 +73,7 @@ SYMBOLS = {
                                  c_void_p]),
     "mmcl_positive_logits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                      c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmcl_logit_scale": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "mmcl_indexed_similarity": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                         c_void_p, c_void_p, c_void_p, c_double, c_void_p,
                                         c_void_p]),

@@ -365,6 +365,18 @@ int mmcl_positive_logits(mmcl_handle* h, const void* q_bf16, int64_t nq, const v
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_positive_logits");
 }
 
+int mmcl_logit_scale(mmcl_handle* h, float* log_scale, int64_t n, double max_scale,
+                     float* scale_out, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_logit_scale: null handle");
+  REQUIRE(n >= 0 && (n == 0 || (log_scale && scale_out)), "mmcl_logit_scale: bad arguments");
+  REQUIRE(max_scale >= 1.0, "mmcl_logit_scale: max_scale must be >= 1");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_logit_scale(log_scale, n, max_scale, scale_out,
+                                     static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_logit_scale");
+}
+
 int mmcl_indexed_similarity(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
                             int64_t nk, int64_t d, const int64_t* index, const float* qinv,
                             const float* kinv, double add, float* out, mmcl_stream stream) {

@@ -88,6 +88,16 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, long long src_row
   if (inv_norm && lane == 0) inv_norm[row] = inv;
 }
 
+// log_s <- clamp(log_s, 0, log(max)) in place; s = exp(log_s)   (the caller glue of the task)
+__global__ void logit_scale_kernel(float* __restrict__ log_s, long long n, float max_log,
+                                   float* __restrict__ s_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fminf(fmaxf(log_s[i], 0.f), max_log);
+  log_s[i] = v;
+  s_out[i] = expf(v);
+}
+
 __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long long nq,
                                        const __nv_bfloat16* __restrict__ k, long long nk, int d,
                                        long long label_offset, const float* __restrict__ scale,
@@ -297,6 +307,15 @@ cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, l
   positive_logits_kernel<<<unsigned((nq + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(q), nq, static_cast<const __nv_bfloat16*>(k), nk, int(d),
       label_offset, scale, qinv, kinv, pos, nullptr, 0.f);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_logit_scale(float* log_s, long long n, double max_scale, float* s_out,
+                               cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  logit_scale_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(log_s, n, float(log(max_scale)),
+                                                                   s_out);
   count_launches(1);
   return cudaGetLastError();
 }

@@ -48,6 +48,8 @@ cudaError_t launch_positive_logits(const void* q, long long nq, const void* k, l
                                    long long d, long long label_offset, const float* scale,
                                    const float* qinv, const float* kinv, float* pos,
                                    cudaStream_t stream);
+cudaError_t launch_logit_scale(float* log_s, long long n, double max_scale, float* s_out,
+                               cudaStream_t stream);
 cudaError_t launch_indexed_similarity(const void* q, long long nq, const void* k, long long nk,
                                       long long d, const int64_t* index, const float* qinv,
                                       const float* kinv, float add, float* out,
