@@ -123,8 +123,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_GLOBAL)
-    ap.add_argument("--d", type=int, default=DIM)
+    # (full-length names: torchrun's own parser treats unknown prefixes such as --n as ambiguous)
+    ap.add_argument("--global-batch", dest="n", type=int, default=N_GLOBAL)
+    ap.add_argument("--embed-dim", dest="d", type=int, default=DIM)
     ap.add_argument("--cpu-rows", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

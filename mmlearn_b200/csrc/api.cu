@@ -435,7 +435,8 @@ int mmcl_sim_grad_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void
   int rc = check_sim_args("mmcl_sim_grad_bwd", x_bf16, nx, y_bf16, ny, d);
   if (rc) return rc;
   if (nx == 0 || ny == 0) return MMCL_OK;
-  REQUIRE(dx, "mmcl_sim_grad_bwd: null dx");
+  REQUIRE(dx && (reinterpret_cast<uintptr_t>(dx) & 15) == 0,
+          "mmcl_sim_grad_bwd: dx must be non-null and 16-byte aligned");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   const char* err = nullptr;
@@ -455,7 +456,8 @@ int mmcl_sim_grad_bwd_lse(mmcl_handle* h, const void* x_bf16, int64_t nx, const 
   int rc = check_sim_args("mmcl_sim_grad_bwd_lse", x_bf16, nx, y_bf16, ny, d);
   if (rc) return rc;
   if (nx == 0) return MMCL_OK;
-  REQUIRE(dx, "mmcl_sim_grad_bwd_lse: null dx");
+  REQUIRE(dx && (reinterpret_cast<uintptr_t>(dx) & 15) == 0,
+          "mmcl_sim_grad_bwd_lse: dx must be non-null and 16-byte aligned");
   REQUIRE((!lse_row || row_den > 0) && (!lse_col || col_den > 0),
           "mmcl_sim_grad_bwd_lse: denominators must be positive");
   std::lock_guard<std::mutex> lk(h->mu);

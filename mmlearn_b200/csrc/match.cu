@@ -313,7 +313,11 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
   return cudaGetLastError();
 }
 
-size_t identity_check_workspace_bytes(long long m) { return size_t(table_size(m > 0 ? m : 1)) * 4; }
+// The identity check is a single dependent-probe pass, so its duration is the LONGEST probe chain:
+// a sparser table (load factor 1/8 instead of 1/2) keeps chains to 1-3 steps.
+static long long identity_table_size(long long m) { return 4 * table_size(m > 0 ? m : 1); }
+
+size_t identity_check_workspace_bytes(long long m) { return size_t(identity_table_size(m)) * 4; }
 
 cudaError_t launch_identity_check(const int64_t* ids_a, long long n, const int64_t* ids_b,
                                   long long m, int64_t* out_info, void* workspace,
@@ -322,7 +326,7 @@ cudaError_t launch_identity_check(const int64_t* ids_a, long long n, const int64
   info_init_kernel<<<1, 1, 0, stream>>>(info, n, m, 1);
   count_launches(1);
   if (n != m || n == 0) return cudaGetLastError();
-  const long long T = table_size(m);
+  const long long T = identity_table_size(m);
   if (size_t(T) * 4 > workspace_bytes) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(workspace, 0xFF, size_t(T) * 4, stream);  // owner = -1
   if (e != cudaSuccess) return e;

@@ -346,9 +346,10 @@ sim_grad_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_ld_wait();
         if (grow < p.nx) {
           float* dst = p.dx + (long long)grow * p.d + dc * DC + ch * 32;
+          // d % 8 == 0 (checked by the ABI): groups of 4 columns are whole and 16-byte aligned
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (ch * 32 + e < ncols) atomicAdd(dst + e, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; e += 4)
+            if (ch * 32 + e < ncols) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
         }
       }
       tc_fence_before();

@@ -500,7 +500,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           if (grow < p.nx) {
             float* dst = p.dx + (long long)grow * p.d + col0 + ch * 32;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+            for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
           }
         }
         tc_fence_before();

@@ -344,6 +344,15 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
 }
 // asynchronous 16-byte store into a (peer) CTA's shared memory; completes 16 tx-bytes on the
 // mbarrier at `cluster_mbar` (same CTA as the destination).  No fence needed by the writer.
+// fp32 reduction of 4 consecutive words (sm_90+: one REDG.F32x4 instead of four scalar atomics);
+// the address must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* addr, uint32_t a, uint32_t b, uint32_t c,
+                                           uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b,
                                             uint32_t c, uint32_t d, uint32_t cluster_mbar) {
   asm volatile(
