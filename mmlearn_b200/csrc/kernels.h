@@ -73,26 +73,30 @@ cudaError_t launch_match_ids(const int64_t* ids_a, long long n, const int64_t* i
                              void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // symm.cu: symmetric peer-memory arena (CUDA IPC over NVLink)
+constexpr int kFenceChannels = 4;
 struct SymmArena {
   char* local = nullptr;       // [flags 1 KB][buffer 0][buffer 1]
   std::vector<char*> peers;    // base of every rank's allocation (own entry = local)
   char** d_peers = nullptr;    // the same table on the device
   void* scratch = nullptr;     // setup-time staging (IPC handle exchange, barriers)
   size_t bytes = 0;            // usable bytes per buffer
-  unsigned long long seq = 0;  // fence sequence number
+  unsigned long long seq[4] = {0, 0, 0, 0};  // fence sequence number per channel
   bool failed = false;
 };
 int symm_reserve(SymmArena* a, void* nccl_comm, int rank, int world, size_t bytes,
                  cudaStream_t stream, std::string* err);
 void symm_destroy(SymmArena* a, int rank);
 char* symm_buffer(const SymmArena* a, int parity);
+// skip_rank >= 0: that rank's buffer is not written (its copy is the source itself)
 cudaError_t launch_symm_put(const SymmArena* a, int world, int parity, const void* src,
-                            size_t bytes, size_t dst_off, cudaStream_t stream);
+                            size_t bytes, size_t dst_off, cudaStream_t stream, int skip_rank = -1);
 cudaError_t launch_pack_rows_symm(const SymmArena* a, int world, int parity, const void* src,
                                   int src_dtype, long long src_rows, long long d,
                                   const int64_t* idx, long long n_out, int normalize,
                                   size_t off_rows, long long off_inv, cudaStream_t stream);
-cudaError_t launch_symm_fence(SymmArena* a, int world, int rank, cudaStream_t stream);
+// Fences of different channels use different flag words and may overlap (different streams).
+cudaError_t launch_symm_fence(SymmArena* a, int world, int rank, cudaStream_t stream,
+                              int channel = 0);
 
 size_t identity_check_workspace_bytes(long long m);
 cudaError_t launch_identity_check(const int64_t* ids_a, long long n, const int64_t* ids_b,

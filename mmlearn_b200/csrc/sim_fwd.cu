@@ -211,10 +211,21 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int cv = valid - ch * 32;
             const float* kc = kv + ch * 32;
             const long long tl = tg - ((long long)kt * BN + ch * 32);  // the positive's slot, if here
-            const int tloc = (tl >= 0 && tl < 32) ? int(tl) : -1;
+            if (cv >= 32 && (tl < 0 || tl >= 32)) {
+              // common case: whole chunk, positive elsewhere -> FMUL + FSETP + predicated FADD
+              float c0 = 0.f, c1 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              cnt += (e < cv && e != tloc && __uint_as_float(v[e]) * kc[e] > th) ? 1 : 0;
+              for (int e = 0; e < 32; e += 2) {
+                if (__uint_as_float(v[e]) * kc[e] > th) c0 += 1.f;
+                if (__uint_as_float(v[e + 1]) * kc[e + 1] > th) c1 += 1.f;
+              }
+              cnt += int(c0 + c1);
+            } else {
+              const int tloc = (tl >= 0 && tl < 32) ? int(tl) : -1;
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                cnt += (e < cv && e != tloc && __uint_as_float(v[e]) * kc[e] > th) ? 1 : 0;
+            }
           }
           ++acc;
         }

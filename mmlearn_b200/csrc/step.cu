@@ -11,7 +11,15 @@
 //   [table: W x P x 4 int64][ids of every key modality: N x 2 int64][rows: N x d bf16 and
 //   inverse norms: N f32 per modality][lse_a, lse_b: N f32 per pair]
 // with N = world * rows.  Offsets are fixed at mmcl_step_create and identical on all ranks.
+//
+// Overlap (world > 1).  The first kernel of the step (direction a of pair 0) needs the local rows
+// of its query modality and ALL rows of its key modality.  Only the key modality is therefore
+// pushed to the peers before the first fence; every other modality is packed into the LOCAL slot
+// only, and a side stream pushes it to the peers (and runs its own fence, on a separate flag
+// channel) while the main stream already computes direction a.  The main stream joins the side
+// stream before the first kernel that reads remote rows of those modalities.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -54,6 +62,11 @@ struct mmcl_step {
   cudaEvent_t ev = nullptr;
   bool pending = false;
   bool last_local_ok = false;
+  // overlap of the second-wave pushes with the first similarity kernel
+  bool overlap = false;
+  int first_key = -1;  // modality whose rows every rank needs before anything can start
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -227,8 +240,20 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
   DeviceGuard g(h->device);
   cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&s->host), s->host_words * 8);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
+  s->first_key = s->pairs[0].mod_b;
+  const char* no_ov = getenv("MMCL_NO_OVERLAP");
+  s->overlap = W > 1 && s->M > 1 && !(no_ov && no_ov[0] == '1');
+  if (e == cudaSuccess && s->overlap) {
+    e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     if (s->host) cudaFreeHost(s->host);
+    if (s->ev) cudaEventDestroy(s->ev);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     delete s;
     return cuda_fail(e, "mmcl_step_create");
   }
@@ -240,6 +265,12 @@ int mmcl_step_destroy(mmcl_step* s) {
   if (!s) return MMCL_OK;
   DeviceGuard g(s->h->device);
   if (s->ev) cudaEventDestroy(s->ev);
+  if (s->side) {
+    cudaStreamSynchronize(s->side);
+    cudaStreamDestroy(s->side);
+  }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->host) cudaFreeHost(s->host);
   delete s;
   return MMCL_OK;
@@ -301,6 +332,7 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
   // (local_ok == 0: the zeroed rows never equal the assumed {rows, 1, rows, rows})
 
   // ---- 2. pack rows (and publish table, ids, rows, norms to every rank) ----
+  bool joined = true;  // false while the side stream still pushes second-wave modalities
   if (W > 1) {
     CU(launch_symm_put(&h->arena, W, parity, info, size_t(s->P) * 32,
                        s->ar_table + size_t(h->rank) * s->P * 32, st),
@@ -311,12 +343,39 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
           CU(launch_symm_put(&h->arena, W, parity, ids[m], size_t(b) * 16,
                              s->ar_ids[m] + size_t(off) * 16, st),
              "mmcl_step_forward (ids)");
-        CU(launch_pack_rows_symm(&h->arena, W, parity, emb[m], s->dtype[m], b, d, nullptr, b,
-                                 s->normalize, s->ar_rows[m] + size_t(off) * d * 2,
-                                 s->normalize ? (long long)(s->ar_inv[m] + size_t(off) * 4) : -1,
-                                 st),
-           "mmcl_step_forward (pack)");
+        const size_t o_rows = s->ar_rows[m] + size_t(off) * d * 2;
+        const size_t o_inv = s->ar_inv[m] + size_t(off) * 4;
+        if (!s->overlap || m == s->first_key) {
+          CU(launch_pack_rows_symm(&h->arena, W, parity, emb[m], s->dtype[m], b, d, nullptr, b,
+                                   s->normalize, o_rows, s->normalize ? (long long)o_inv : -1, st),
+             "mmcl_step_forward (pack)");
+        } else {  // second wave: local slot now, peers from the side stream
+          CU(launch_pack_rows(emb[m], s->dtype[m], b, d, nullptr, b, s->normalize, v.ar + o_rows,
+                              s->normalize ? reinterpret_cast<float*>(v.ar + o_inv) : nullptr, st),
+             "mmcl_step_forward (pack local)");
+        }
       }
+    if (s->overlap) {
+      // every rank walks through the side-stream fence, whatever its local state
+      CU(cudaEventRecord(s->ev_fork, st), "mmcl_step_forward (fork)");
+      CU(cudaStreamWaitEvent(s->side, s->ev_fork, 0), "mmcl_step_forward (fork wait)");
+      if (local_ok)
+        for (int m = 0; m < s->M; ++m) {
+          if (m == s->first_key) continue;
+          const size_t o_rows = s->ar_rows[m] + size_t(off) * d * 2;
+          const size_t o_inv = s->ar_inv[m] + size_t(off) * 4;
+          CU(launch_symm_put(&h->arena, W, parity, v.ar + o_rows, size_t(b) * d * 2, o_rows,
+                             s->side, h->rank),
+             "mmcl_step_forward (push rows)");
+          if (s->normalize)
+            CU(launch_symm_put(&h->arena, W, parity, v.ar + o_inv, size_t(b) * 4, o_inv, s->side,
+                               h->rank),
+               "mmcl_step_forward (push norms)");
+        }
+      CU(launch_symm_fence(&h->arena, W, h->rank, s->side, 1), "mmcl_step_forward (side fence)");
+      CU(cudaEventRecord(s->ev_join, s->side), "mmcl_step_forward (join record)");
+      joined = false;
+    }
     CU(launch_symm_fence(&h->arena, W, h->rank, st), "mmcl_step_forward (fence)");
   } else if (local_ok) {
     for (int m = 0; m < s->M; ++m)
@@ -326,6 +385,11 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
                           st),
          "mmcl_step_forward (pack)");
   }
+  auto join = [&]() -> cudaError_t {
+    if (joined) return cudaSuccess;
+    joined = true;
+    return cudaStreamWaitEvent(st, s->ev_join, 0);
+  };
 
   if (local_ok) {
     // ---- 3. cross-rank duplicate check on the gathered ids of every key modality ----
@@ -353,8 +417,11 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
       const float* ia = ia_all ? ia_all + off : nullptr;
       const float* ib = ib_all ? ib_all + off : nullptr;
       const char* err = nullptr;
+      // direction a of pair 0 reads remote rows of the first-wave modality only
+      if (!(p == 0 && pr.mod_b == s->first_key)) CU(join(), "mmcl_step_forward (join)");
       e = launch_sim_lse_fwd(h->num_sms, fa, b, fb_all, N, d, sp, ia, ib_all, lse_a, es_a,
                              v.ws + s->off_fws, s->fws_bytes, st, &err);
+      if (e == cudaSuccess) e = join();
       if (e == cudaSuccess)
         e = launch_sim_lse_fwd(h->num_sms, fb, b, fa_all, N, d, sp, ib, ia_all, lse_b, es_b,
                                v.ws + s->off_fws, s->fws_bytes, st, &err);
@@ -367,6 +434,7 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
          "mmcl_step_forward (pair loss)");
     }
   }
+  CU(join(), "mmcl_step_forward (join)");  // (also on ranks that only go through the motions)
   if (s->all_reduce_loss) {
     ncclResult_t r = ncclAllReduce(out2, out2, size_t(s->P) * 2, ncclFloat, ncclSum, h->comm, st);
     if (r != ncclSuccess) return nccl_fail(r, "mmcl_step_forward (all-reduce)");

@@ -26,15 +26,17 @@ namespace mmcl {
 
 namespace {
 
-constexpr size_t kFlagBytes = 1024;
+constexpr size_t kFlagBytes = 1024;  // kFenceChannels x kMaxRanks 64-bit flag words
+constexpr int kMaxRanks = 32;
 
 template <typename V>  // uint4 (16-byte units) or uint32_t (4-byte units)
 __global__ void symm_put_kernel(char* const* __restrict__ peers, int world, size_t dst_off,
-                                const V* __restrict__ src, size_t n) {
+                                const V* __restrict__ src, size_t n, int skip_rank) {
   const size_t total = n * size_t(world);
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += size_t(gridDim.x) * blockDim.x) {
     const int r = int(i / n);
+    if (r == skip_rank) continue;  // (the source already is that rank's copy)
     const size_t e = i % n;
     reinterpret_cast<V*>(peers[r] + dst_off)[e] = src[e];
   }
@@ -50,13 +52,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // one block, one thread per rank
+// `slot0` = first flag word of the fence channel (kMaxRanks words per channel): fences of
+// different channels may be in flight at the same time on different streams.
 __global__ void symm_fence_kernel(char* const* __restrict__ peers, int world, int rank,
-                                  unsigned long long seq) {
+                                  unsigned long long seq, int slot0) {
   const int r = threadIdx.x;
   if (r < world) {
     __threadfence_system();  // everything this stream wrote to peer memory before the fence
-    st_release_sys(reinterpret_cast<unsigned long long*>(peers[r]) + rank, seq);
-    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers[rank]) + r;
+    st_release_sys(reinterpret_cast<unsigned long long*>(peers[r]) + slot0 + rank, seq);
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(peers[rank]) + slot0 + r;
     while (ld_acquire_sys(mine) < seq) {
     }
   }
@@ -246,7 +251,7 @@ int symm_reserve(SymmArena* a, void* comm_v, int rank, int world, size_t bytes,
   a->peers = peers;
   a->local = base;
   a->bytes = bytes;
-  a->seq = 0;
+  for (auto& q : a->seq) q = 0;
   return 0;
 }
 
@@ -266,7 +271,7 @@ char* symm_buffer(const SymmArena* a, int parity) {
 }
 
 cudaError_t launch_symm_put(const SymmArena* a, int world, int parity, const void* src,
-                            size_t bytes, size_t dst_off, cudaStream_t stream) {
+                            size_t bytes, size_t dst_off, cudaStream_t stream, int skip_rank) {
   if (bytes == 0) return cudaSuccess;
   const size_t off = kFlagBytes + size_t(parity & 1) * a->bytes + dst_off;
   const bool v16 = bytes % 16 == 0 && dst_off % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -276,10 +281,11 @@ cudaError_t launch_symm_put(const SymmArena* a, int world, int parity, const voi
   if (blocks > 1184) blocks = 1184;
   if (v16)
     symm_put_kernel<uint4><<<blocks, 256, 0, stream>>>(a->d_peers, world, off,
-                                                       static_cast<const uint4*>(src), n);
+                                                       static_cast<const uint4*>(src), n, skip_rank);
   else
     symm_put_kernel<uint32_t><<<blocks, 256, 0, stream>>>(a->d_peers, world, off,
-                                                          static_cast<const uint32_t*>(src), n);
+                                                          static_cast<const uint32_t*>(src), n,
+                                                          skip_rank);
   count_launches(1);
   return cudaGetLastError();
 }
@@ -303,9 +309,12 @@ cudaError_t launch_pack_rows_symm(const SymmArena* a, int world, int parity, con
   return cudaGetLastError();
 }
 
-cudaError_t launch_symm_fence(SymmArena* a, int world, int rank, cudaStream_t stream) {
-  a->seq += 1;
-  symm_fence_kernel<<<1, 32 * ((world + 31) / 32), 0, stream>>>(a->d_peers, world, rank, a->seq);
+cudaError_t launch_symm_fence(SymmArena* a, int world, int rank, cudaStream_t stream,
+                              int channel) {
+  if (channel < 0 || channel >= kFenceChannels || world > kMaxRanks) return cudaErrorInvalidValue;
+  a->seq[channel] += 1;
+  symm_fence_kernel<<<1, 32 * ((world + 31) / 32), 0, stream>>>(a->d_peers, world, rank,
+                                                                a->seq[channel], channel * kMaxRanks);
   count_launches(1);
   return cudaGetLastError();
 }
