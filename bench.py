@@ -144,9 +144,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # This program's stdout is the one JSON line: anything libraries print on fd 1 while the
+    # bench runs (NCCL's version banner, for one) goes to stderr instead.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner on stdout; this program's stdout is the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     warmup = max(args.warmup, 3)
@@ -347,7 +350,10 @@ def main():
             "torch_gpu_baseline": lib_gpu,
             "loss": loss_value,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
