@@ -19,7 +19,9 @@ DEV = "cuda:0"
 def test_head_matches_reference_task_arithmetic(init, max_scale):
     from mmlearn_b200.task import ContrastiveLossHead
 
-    emb, ids = synthetic_inputs(768, 256)
+    # uncorrelated pairs: with correlated ones the loss at the clamp (s = 100) is ~1e-6 and
+    # relative tolerances are meaningless
+    emb, ids = synthetic_inputs(768, 256, correlated=False)
     s_eff = min(max(init, 1.0), max_scale)  # clamp(log s, 0, log max)
     # the reference task normalises in encode() and the loss normalises again: idempotent
     ref = contrastive_oracle(emb, ids, s_eff, [OPair(("rgb", "text"))], l2_normalize=True,
