@@ -32,7 +32,7 @@ _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 def table_rows(table: list, world: int, n_pairs: int) -> Optional[int]:
     """``rows`` if the match table (nested list [world][P][4] = k, identity, n, m) describes the
     steady state (k = n = m = rows > 0 and identity, everywhere), else None."""
-    rows = table[0][0][0] if n_pairs > 0 else 0
+    rows = table[0][0][0] if (n_pairs > 0 and table) else 0
     if rows <= 0:
         return None
     want = [rows, 1, rows, rows]

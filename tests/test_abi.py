@@ -35,6 +35,14 @@ def test_library_loads_and_exports_every_symbol():
     assert lib.mmcl_match_workspace_bytes(10, 10) > 0
     assert lib.mmcl_nccl_unique_id(None) == -1
     assert b"null uid" in lib.mmcl_last_error()
+    # the step executor validates before touching CUDA as well
+    assert lib.mmcl_step_workspace_bytes(None) == 0 and lib.mmcl_step_arena_bytes(None) == 0
+    assert lib.mmcl_step_create(None, None, None) == -1
+    assert b"mmcl_step_create" in lib.mmcl_last_error()
+    assert lib.mmcl_step_verify(None, None) == -1
+    assert lib.mmcl_step_destroy(None) == 0
+    assert lib.mmcl_sim_rank_fwd(None, None, 0, None, 0, 8, None, None, None, None, None, None, 0,
+                                 None) == -1
 
 
 def test_no_cpu_fallback():

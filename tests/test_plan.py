@@ -90,3 +90,19 @@ def test_count_exchange_two_ranks_gloo():
         assert table == [[10, 0, 7], [11, 1, 7]]
         assert off == (0 if r == 0 else 10)
         assert labels == (list(range(10)) if r == 0 else list(range(10, 21)))
+
+
+def test_steady_state_table_detection():
+    """mmlearn_b200.steady.table_rows: the native step executor is only armed when EVERY rank
+    reports [rows, identity=1, rows, rows] for EVERY pair with the same rows > 0."""
+    from mmlearn_b200.steady import table_rows
+
+    ok = [[[64, 1, 64, 64], [64, 1, 64, 64]], [[64, 1, 64, 64], [64, 1, 64, 64]]]
+    assert table_rows(ok, 2, 2) == 64
+    for r, p, col, val in [(1, 0, 0, 63), (0, 1, 1, 0), (1, 1, 2, 65), (0, 0, 3, 60)]:
+        bad = [[list(x) for x in row] for row in ok]
+        bad[r][p][col] = val
+        assert table_rows(bad, 2, 2) is None
+    assert table_rows([[[0, 1, 0, 0]]], 1, 1) is None      # nobody has the pair
+    assert table_rows([[[12, 1, 12, 12]], [[20, 1, 20, 20]]], 2, 1) is None  # uneven ranks
+    assert table_rows([], 1, 0) is None
