@@ -245,54 +245,54 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
         const int valid = p.nk - kt * BN;  // columns of this tile that exist (>= 1)
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          uint32_t v[32];
-          tmem_ld_x32(taddr + ch * 32, v);
-          tmem_ld_wait();
-          if (ch == BN / 32 - 1) {
-            tc_fence_before();
-            mbar_arrive(&acc_empty[ab]);
-          }
+        // One 32-column chunk: multiply by the key factors, update the running maximum, add the
+        // exponentials.  Packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2) with two interleaved
+        // partial sums halves the FP32 instruction count next to the MUFU work.
+        auto process = [&](uint32_t (&v)[32], int ch) {
           const int cv = valid - ch * 32;
+          float2 x2[16];
           {
             const float4* k4 = reinterpret_cast<const float4*>(kv + ch * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 f = k4[e4];
-              v[4 * e4 + 0] = __float_as_uint(__uint_as_float(v[4 * e4 + 0]) * f.x);
-              v[4 * e4 + 1] = __float_as_uint(__uint_as_float(v[4 * e4 + 1]) * f.y);
-              v[4 * e4 + 2] = __float_as_uint(__uint_as_float(v[4 * e4 + 2]) * f.z);
-              v[4 * e4 + 3] = __float_as_uint(__uint_as_float(v[4 * e4 + 3]) * f.w);
+              x2[2 * e4] = __fmul2_rn(make_float2(__uint_as_float(v[4 * e4]),
+                                                  __uint_as_float(v[4 * e4 + 1])),
+                                      make_float2(f.x, f.y));
+              x2[2 * e4 + 1] = __fmul2_rn(make_float2(__uint_as_float(v[4 * e4 + 2]),
+                                                      __uint_as_float(v[4 * e4 + 3])),
+                                          make_float2(f.z, f.w));
             }
           }
           if (cv >= 32) {
-            float ext = __uint_as_float(v[0]);
+            float ext = x2[0].x;
             if (!neg) {
 #pragma unroll
-              for (int e = 1; e < 32; ++e) ext = fmaxf(ext, __uint_as_float(v[e]));
+              for (int e = 0; e < 16; ++e) ext = fmaxf(ext, fmaxf(x2[e].x, x2[e].y));
             } else {
 #pragma unroll
-              for (int e = 1; e < 32; ++e) ext = fminf(ext, __uint_as_float(v[e]));
+              for (int e = 0; e < 16; ++e) ext = fminf(ext, fminf(x2[e].x, x2[e].y));
             }
             const float mn = fmaxf(m, ext * c);
             const float alpha = ex2f(m - mn);
-            l *= alpha;
-            tt *= alpha;
             m = mn;
+            const float2 c2 = make_float2(c, c), nm2 = make_float2(-m, -m);
+            float2 l2 = make_float2(l * alpha, 0.f), t2 = make_float2(tt * alpha, 0.f);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float x = __uint_as_float(v[e]);
-              const float pe = ex2f(fmaf(x, c, -m));
-              l += pe;
-              tt = fmaf(pe, x, tt);
+            for (int e = 0; e < 16; ++e) {
+              const float2 a = __ffma2_rn(x2[e], c2, nm2);
+              const float2 pe = make_float2(ex2f(a.x), ex2f(a.y));
+              l2 = __fadd2_rn(l2, pe);
+              t2 = __ffma2_rn(pe, x2[e], t2);
             }
+            l = l2.x + l2.y;
+            tt = t2.x + t2.y;
           } else if (cv > 0) {
             // ragged last tile: only the first cv columns exist
             float ext = neg ? INFINITY : -INFINITY;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const float x = __uint_as_float(v[e]);
+              const float x = (e & 1) ? x2[e >> 1].y : x2[e >> 1].x;
               if (e < cv) ext = neg ? fminf(ext, x) : fmaxf(ext, x);
             }
             const float mn = fmaxf(m, ext * c);
@@ -302,7 +302,7 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             m = mn;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const float x = __uint_as_float(v[e]);
+              const float x = (e & 1) ? x2[e >> 1].y : x2[e >> 1].x;
               if (e < cv) {
                 const float pe = ex2f(fmaf(x, c, -m));
                 l += pe;
@@ -310,6 +310,24 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
             }
           }
+        };
+        // Software pipeline over chunk pairs: the tensor-memory load of the next chunk is in
+        // flight while the current one is reduced.
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(taddr, va);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ch += 2) {
+          tmem_ld_wait();
+          tmem_ld_x32(taddr + (ch + 1) * 32, vb);
+          process(va, ch);
+          tmem_ld_wait();
+          if (ch + 2 < BN / 32) {
+            tmem_ld_x32(taddr + (ch + 2) * 32, va);
+          } else {  // every column of this accumulator has been read
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+          }
+          process(vb, ch + 1);
         }
         ++acc;
       }
