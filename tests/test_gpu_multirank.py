@@ -204,3 +204,83 @@ def test_native_step_structure_change_on_one_rank():
         mp.spawn(_worker_sequence, args=(2, names, os.path.join(td, "init"), ret), nprocs=2,
                  join=True)
     _check_sequence(names, ret, [0, 1, 1, 1, 1, 2, 3])
+
+
+def _worker_recall(rank, world, init_file, ret):
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world,
+                            device_id=dev)
+    from mmlearn_b200 import RetrievalRecallAtK
+
+    xs, ys, idxs = _recall_data()
+    met = RetrievalRecallAtK(top_k=5, reduction="none")
+    for t in range(len(xs)):
+        met.update(xs[t][rank].to(dev), ys[t][rank].to(dev), idxs[t][rank].to(dev))
+    ret[rank] = {"value": {k: float(met.compute(k)) for k in (1, 5, 20)},
+                 "hits5": met.hits().cpu().numpy(), "ranks": met.ranks().cpu().numpy()}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _recall_data():
+    """Two update steps with uneven per-rank batches; positives permuted inside each rank's batch."""
+    g = torch.Generator().manual_seed(21)
+    sizes = [[40, 56], [64, 24]]  # sizes[t][r]
+    xs, ys, idxs = [], [], []
+    for row in sizes:
+        xt, yt, it = [], [], []
+        for n in row:
+            x = torch.randn(n, 64, generator=g).to(torch.bfloat16).float()
+            y = (0.3 * x + torch.randn(n, 64, generator=g)).to(torch.bfloat16).float()
+            p = torch.randperm(n, generator=g)
+            yp = torch.empty_like(y)
+            yp[p] = y
+            xt.append(x)
+            yt.append(yp)
+            it.append(p)
+        xs.append(xt)
+        ys.append(yt)
+        idxs.append(it)
+    return xs, ys, idxs
+
+
+def test_retrieval_recall_two_ranks():
+    """Distributed RetrievalRecallAtK: every rank ranks its own queries against the all-gathered
+    database; the global row order and index offsets are the reference's (update(),
+    retrieval_recall.py:137-160), checked against the single-process oracle on the data laid out
+    in that order."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle.retrieval_oracle import recall_at_k_oracle
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_recall, args=(2, os.path.join(td, "init"), ret), nprocs=2, join=True)
+    xs, ys, idxs = _recall_data()
+    # what the reference's update() accumulates: per step, the ranks' batches concatenated, the
+    # local indexes shifted by the rows of lower ranks (the oracle adds the rows of earlier steps)
+    gx = [torch.cat(x) for x in xs]
+    gy = [torch.cat(y) for y in ys]
+    gi = [torch.cat([i + sum(len(q) for q in ib[:r]) for r, i in enumerate(ib)]) for ib in idxs]
+    for k in (1, 5, 20):
+        value, hits, ranks = recall_at_k_oracle(gx, gy, gi, k)
+        for r in range(2):
+            assert ret[r]["value"][k] == pytest.approx(value, abs=1e-6)
+    value, hits, ranks = recall_at_k_oracle(gx, gy, gi, 5)
+    # slice the oracle's global order (step-major, then rank) back into per-rank query order
+    pos = 0
+    per_rank = [[], []]
+    for t in range(len(xs)):
+        for r in range(2):
+            n = len(xs[t][r])
+            per_rank[r].append((hits[pos:pos + n], ranks[pos:pos + n]))
+            pos += n
+    for r in range(2):
+        assert np.array_equal(ret[r]["hits5"], np.concatenate([h for h, _ in per_rank[r]]))
+        assert np.array_equal(ret[r]["ranks"], np.concatenate([q for _, q in per_rank[r]]))
