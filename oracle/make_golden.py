@@ -106,6 +106,14 @@ def build_cases():
     cases["w2_rank1_unpaired"] = dict(
         world=2, emb=embs, ids=idss, scale=1 / 0.07, pairs=[("rgb", "text", 1.0)],
         flags=dict(l2_normalize=True, local_loss=True, gather_with_grad=False, cache_labels=False))
+    # 6b. two ranks, rank 1 does not have the text modality at all (placeholder path of
+    # _gather_dicts, contrastive.py:471-480,495); gather_with_grad=False for the reason above
+    embs = [{"rgb": a[:16], "text": b[:16]}, {"rgb": a[16:]}]
+    idss = [{"rgb": _ids(np.zeros(16), np.arange(16)), "text": _ids(np.zeros(16), np.arange(16))},
+            {"rgb": _ids(np.zeros(16), np.arange(16, 32))}]
+    cases["w2_rank1_missing_modality"] = dict(
+        world=2, emb=embs, ids=idss, scale=1 / 0.07, pairs=[("rgb", "text", 1.0)],
+        flags=dict(l2_normalize=True, local_loss=True, gather_with_grad=False, cache_labels=False))
     # 7. modality_alignment term (contrastive.py:344-413).  Unequal modality sizes in the
     # three-modality case exercise the reference's block-offset rule.
     n, d = 12, 32
