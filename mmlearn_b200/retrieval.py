@@ -219,3 +219,13 @@ class RetrievalRecallAtK(nn.Module):
     def forward(self, *args: Any, **kwargs: Any) -> Any:
         """Forward method is not supported (as in the reference, retrieval_recall.py:225-236)."""
         raise NotImplementedError("RetrievalRecallAtK metric does not support forward method")
+
+
+try:  # pragma: no cover - hydra-zen / mmlearn are not installable in the build image
+    from mmlearn.conf import external_store  # type: ignore
+
+    # the reference registers its metric in group "modules/metrics" (retrieval_recall.py:20)
+    external_store(RetrievalRecallAtK, name="FusedRetrievalRecallAtK", group="modules/metrics",
+                   provider="mmlearn_b200")
+except Exception:  # noqa: BLE001
+    pass
