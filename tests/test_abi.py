@@ -55,3 +55,20 @@ def test_no_cpu_fallback():
         fn({"rgb_embedding": torch.randn(4, 8), "text_embedding": torch.randn(4, 8)},
            {"rgb": torch.zeros(4, 2, dtype=torch.long), "text": torch.zeros(4, 2, dtype=torch.long)},
            torch.tensor(1.0), [LossPairSpec(("rgb", "text"))])
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/mmcl.h must compile as C99 (and as C++) on its own,
+    with no torch / CUDA headers."""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "mmcl.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+    txt = open(hdr).read()
+    assert "#include <cuda" not in txt and "#include <torch" not in txt
