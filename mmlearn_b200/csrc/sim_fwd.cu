@@ -1,11 +1,15 @@
 // Forward hot kernel: S = s * Q K^T in 128x256 fp32 tiles that live only in tensor memory,
 // reduced on the fly to per-row (max, sum-exp, sum-exp*logit).
 //
-// Roles (256 threads, 1 CTA / SM, persistent):
+// Roles (384 threads, 1 CTA / SM, persistent):
 //   warp 0    TMA producer  (Q tile resident in smem when it fits, K streamed in 64-wide k-chunks)
 //   warp 1    tcgen05.mma issuer (one elected thread), double-buffered TMEM accumulators
 //   warp 2    TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld -> online log-sum-exp in registers (one row per thread)
+//   warps 4-11 epilogue: tcgen05.ld -> online log-sum-exp in registers.  Two warps per SM
+//             sub-partition: warps 4-7 reduce columns 0-127 of each 128x256 tile, warps 8-11
+//             columns 128-255 (one row per thread, each half gives its own partial statistics).
+//             With one warp per sub-partition the epilogue (dependent ALU latency, MUFU) took
+//             ~6500 cycles per tile against ~4200 for the MMAs (ncu stall samples, round 1).
 // Work distribution: the nqt x nkt tile grid is linearised (q-tile major) and cut into
 // equal contiguous ranges, one per CTA ("stream-K" over the key axis), so all 148 SMs finish
 // together whatever nq is; a row's partial statistics from different CTAs are merged by
@@ -49,7 +53,7 @@ struct FwdParams {
 // counting epilogue -- per row, the number of keys whose similarity exceeds the row's threshold
 // (retrieval rank of the positive, mmcl_sim_rank_fwd); one multiply + compare per logit, no MUFU.
 template <bool kQRes, bool kRank>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -80,7 +84,7 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -169,9 +173,11 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
-    const int q = warp - 4;  // == warp % 4: TMEM lane quadrant
+    const int wg = (warp - 4) >> 2;  // column half of every tile this warpgroup reduces
+    const int q = warp & 3;          // == warp % 4: TMEM lane quadrant
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;
+    const int et = threadIdx.x - 128;  // 0..255: one key factor per thread and tile
+    const int ch0 = wg * (BN / 64);    // first of this warpgroup's BN/64 32-column chunks
     const float s = kRank ? 1.f : *p.scale;
     const bool neg = s < 0.f;
     uint32_t acc = 0;
@@ -181,6 +187,11 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (kt1 > p.nkt) kt1 = p.nkt;
       float m = -INFINITY, l = 0.f, tt = 0.f;
       const int grow = qt * BM + row;
+      float knext;  // key factor of column `et` of the next tile (prefetched one tile ahead)
+      {
+        const int gk = kt0 * BN + et;
+        knext = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+      }
       if (kRank) {
         // count_j [ qinv_i * kinv_j * (q_i . k_j) > thr_i ]  ==  [ x_ij * kinv_j > thr_i / qinv_i ]
         const float qi = (p.qinv && grow < p.nq) ? p.qinv[grow] : 1.f;
@@ -190,21 +201,22 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kt = kt0; kt < kt1; ++kt) {
           const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
           float* kv = sKinv + ab * BN;
-          for (int j = et; j < BN; j += 128) {
-            const int gk = kt * BN + j;
-            kv[j] = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+          kv[et] = knext;  // fetched while the previous tile was being reduced
+          if (kt + 1 < kt1) {
+            const int gk = (kt + 1) * BN + et;
+            knext = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
           mbar_wait(&acc_full[ab], aphase);
           tc_fence_after();
           const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
           const int valid = p.nk - kt * BN;
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = ch0; ch < ch0 + BN / 64; ++ch) {
             uint32_t v[32];
             tmem_ld_x32(taddr + ch * 32, v);
             tmem_ld_wait();
-            if (ch == BN / 32 - 1) {
+            if (ch == ch0 + BN / 64 - 1) {
               tc_fence_before();
               mbar_arrive(&acc_empty[ab]);
             }
@@ -236,11 +248,12 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int kt = kt0; kt < kt1; ++kt) {
         const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
         float* kv = sKinv + ab * BN;
-        for (int j = et; j < BN; j += 128) {
-          const int gk = kt * BN + j;
-          kv[j] = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+        kv[et] = knext;  // fetched while the previous tile was being reduced
+        if (kt + 1 < kt1) {
+          const int gk = (kt + 1) * BN + et;
+          knext = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         mbar_wait(&acc_full[ab], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
@@ -314,14 +327,14 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // Software pipeline over chunk pairs: the tensor-memory load of the next chunk is in
         // flight while the current one is reduced.
         uint32_t va[32], vb[32];
-        tmem_ld_x32(taddr, va);
+        tmem_ld_x32(taddr + ch0 * 32, va);
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ch += 2) {
+        for (int ch = ch0; ch < ch0 + BN / 64; ch += 2) {
           tmem_ld_wait();
           tmem_ld_x32(taddr + (ch + 1) * 32, vb);
           process(va, ch);
           tmem_ld_wait();
-          if (ch + 2 < BN / 32) {
+          if (ch + 2 < ch0 + BN / 64) {
             tmem_ld_x32(taddr + (ch + 2) * 32, va);
           } else {  // every column of this accumulator has been read
             tc_fence_before();
@@ -335,7 +348,7 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // partial statistics of this (q-tile, key range) segment
       const long long first_tile = (long long)qt * p.nkt;
       const int c_first = int(first_tile / p.tiles_per_cta);
-      const int slot = int(blockIdx.x) - c_first;
+      const int slot = 2 * (int(blockIdx.x) - c_first) + wg;  // one partial per column half
       const long long o = (long long)slot * p.part_stride + (long long)qt * BM + row;
       p.part_m[o] = m;
       p.part_l[o] = l;
@@ -356,11 +369,12 @@ __global__ void lse_combine_kernel(FwdParams p, float* __restrict__ lse, float* 
   const long long first_tile = (long long)qt * p.nkt;
   const int c_first = int(first_tile / p.tiles_per_cta);
   const int c_last = int((first_tile + p.nkt - 1) / p.tiles_per_cta);
+  const int nslots = 2 * (c_last - c_first + 1);  // two column halves per CTA segment
   float M = -INFINITY;
-  for (int s = 0; s <= c_last - c_first; ++s)
+  for (int s = 0; s < nslots; ++s)
     M = fmaxf(M, p.part_m[(long long)s * p.part_stride + row]);
   float L = 0.f, T = 0.f;
-  for (int s = 0; s <= c_last - c_first; ++s) {
+  for (int s = 0; s < nslots; ++s) {
     const long long o = (long long)s * p.part_stride + row;
     const float w = exp2f(p.part_m[o] - M);
     L += p.part_l[o] * w;
@@ -380,7 +394,7 @@ __global__ void rank_combine_kernel(FwdParams p, long long* __restrict__ rank) {
   const int c_first = int(first_tile / p.tiles_per_cta);
   const int c_last = int((first_tile + p.nkt - 1) / p.tiles_per_cta);
   long long total = 0;
-  for (int s = 0; s <= c_last - c_first; ++s)
+  for (int s = 0; s < 2 * (c_last - c_first + 1); ++s)
     total += (long long)p.part_m[(long long)s * p.part_stride + row];
   rank[row] = total;
 }
@@ -395,7 +409,7 @@ int fwd_plan(int num_sms, long long nq, long long nk, long long d, FwdParams* p,
   p->total_tiles = (long long)p->nqt * p->nkt;
   long long ctas = p->total_tiles < num_sms ? p->total_tiles : num_sms;
   p->tiles_per_cta = int((p->total_tiles + ctas - 1) / ctas);
-  p->max_slots = (p->nkt + p->tiles_per_cta - 1) / p->tiles_per_cta + 1;
+  p->max_slots = 2 * ((p->nkt + p->tiles_per_cta - 1) / p->tiles_per_cta + 1);  // x2: column halves
   p->part_stride = (long long)p->nqt * BM;
   const size_t budget = 227 * 1024 - 256 /*barriers*/ - 2 * BN * sizeof(float) /*kinv*/;
   *qres = size_t(p->kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= budget;
@@ -435,12 +449,12 @@ cudaError_t launch_fwd(int num_sms, const void* q, long long nq, const void* k, 
     e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true, kRank>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<true, kRank><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
+    sim_lse_fwd_kernel<true, kRank><<<ctas, 384, smem, stream>>>(tmQ, tmK, p);
   } else {
     e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false, kRank>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<false, kRank><<<ctas, 256, smem, stream>>>(tmQ, tmK, p);
+    sim_lse_fwd_kernel<false, kRank><<<ctas, 384, smem, stream>>>(tmQ, tmK, p);
   }
   return cudaGetLastError();
 }
