@@ -28,6 +28,15 @@ sys.path.insert(0, ROOT)
 
 N_GLOBAL = 32768
 DIM = 512
+# BASELINE.json configs 2-4: modalities, pairs (a, b, weight), logit scales
+CONFIGS = {
+    2: dict(n=32768, d=512, mods=["rgb", "text"], pairs=[("rgb", "text", 1.0)], scales=[1 / 0.07]),
+    3: dict(n=131072, d=1024, mods=["rgb", "text"], pairs=[("rgb", "text", 1.0)],
+            scales=[1 / 0.07]),
+    4: dict(n=16384, d=768, mods=["rgb", "dna", "text"],
+            pairs=[("rgb", "dna", 1.0), ("rgb", "text", 0.5), ("dna", "text", 2.0)],
+            scales=[1 / 0.07, 10.0, 50.0]),
+}
 PEAKS_FALLBACK = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
 
 
@@ -87,6 +96,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": reasons}
 
 
+def workload_name(cfg_id, N, d, P, world, weak):
+    base = {2: "BASELINE config 2", 3: "BASELINE config 3", 4: "BASELINE config 4"}[cfg_id]
+    w = (f"ContrastiveLoss fwd+bwd, global batch {N}, d={d}, {P} pair{'s' if P > 1 else ''}, "
+         f"l2_normalize+local_loss+gather_with_grad ({base})")
+    if weak:
+        w += f"; weak-scaling series: {N // world} rows per GPU fixed"
+    return w
+
+
+def metric_name(cfg_id, N, d):
+    if cfg_id == 2 and N == N_GLOBAL and d == DIM:
+        return "contrastive loss fwd+bwd samples/sec @B=32k,d=512"
+    return f"contrastive loss fwd+bwd samples/sec @B={N},d={d} (config {cfg_id})"
+
+
+def resolve(args):
+    """(N, d, modalities, pairs, scales, weak) for this launch."""
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = args.n if args.n else cfg["n"]
+    d = args.d if args.d else cfg["d"]
+    weak = args.rows_per_gpu > 0
+    if weak:
+        N = args.rows_per_gpu * world
+    return N, d, cfg["mods"], cfg["pairs"], cfg["scales"], weak
+
+
 def reference_arm(args):
     """--impl reference: the reference's own CPU arithmetic (pinned oracle port), all host
     threads, on a bounded sample of the same workload (one rank's share: b rows x all N keys)."""
@@ -97,24 +133,43 @@ def reference_arm(args):
 
     from oracle.cpu_reference import time_rank_share
 
+    N, d, mods, pairs, scales, weak = resolve(args)
     b = args.cpu_rows
-    r = time_rank_share(args.n, args.d, b, steps=max(1, args.steps), warmup=min(args.warmup, 1),
-                        threads=os.cpu_count())
+    warm = max(args.warmup, 3)  # same warm-up rule as the repo arm
+    r = time_rank_share(N, d, b, steps=max(1, args.steps), warmup=warm, threads=os.cpu_count())
+    P = len(pairs)
     line = {
-        "impl": "reference", "metric": "contrastive loss fwd+bwd samples/sec @B=32k,d=512",
-        "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ContrastiveLoss fwd+bwd, global batch {args.n}, d={args.d}, 1 pair, "
-                               "l2_normalize+local_loss+gather_with_grad (BASELINE config 2)"},
-        "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"],
-                         "kind": "port",
-                         "sample": f"one rank's share: {b} query rows x all {args.n} keys, both "
-                                   f"directions, fwd+bwd, torch {torch.__version__} CPU fp32"},
-        "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+        "impl": "reference", "metric": metric_name(args.config, N, d),
+        "value": r["samples_per_s"] / P, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warm, "ms_per_step": r["ms_per_step"] * P,
+        "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, N, d, P, args.gpus, weak)},
+        "cpu_baseline": {"value": r["samples_per_s"] / P, "unit": "samples/s",
+                         "cores": r["threads"], "kind": "port",
+                         "sample": f"one rank's share: {b} query rows x all {N} keys, both "
+                                   f"directions, fwd+bwd, one pair timed"
+                                   + (f" and scaled by the {P} pairs" if P > 1 else "")
+                                   + f", torch {torch.__version__} CPU fp32"},
+        "e2e": {"value": r["samples_per_s"] / P, "unit": "samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def ncu_traffic(kernel: str, nx: int, ny: int, d: int):
+    """dram bytes per launch of `kernel` at this shape from the committed ncu captures
+    (profiles/ncu_traffic.json, written by tools/ncu_top.py from `ncu --set full` CSV pages)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        for row in json.load(open(p)):
+            if row["kernel"] == kernel and (row["nx"], row["ny"], row["d"]) == (nx, ny, d):
+                return row["dram_bytes"], row.get("source")
+    except Exception:  # noqa: BLE001
+        pass
+    return None, None
 
 
 def main():
@@ -123,11 +178,16 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config: 2 (headline), 3 (131072 x 1024), 4 (3 modalities)")
     # (full-length names: torchrun's own parser treats unknown prefixes such as --n as ambiguous)
-    ap.add_argument("--global-batch", dest="n", type=int, default=N_GLOBAL)
-    ap.add_argument("--embed-dim", dest="d", type=int, default=DIM)
+    ap.add_argument("--global-batch", dest="n", type=int, default=0)
+    ap.add_argument("--embed-dim", dest="d", type=int, default=0)
+    ap.add_argument("--rows-per-gpu", type=int, default=0,
+                    help="weak-scaling series: fixed rows per GPU, global batch = rows x GPUs")
     ap.add_argument("--cpu-rows", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -136,7 +196,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mmlearn_b200 import ContrastiveLoss, LossPairSpec, _lib, get_handle
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec, Modalities, _lib, get_handle
     from mmlearn_b200._lib import check, ptr
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,32 +213,47 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     warmup = max(args.warmup, 3)
-    N, d = args.n, args.d
+    N, d, mods, pair_cfg, scales, weak = resolve(args)
     assert N % world == 0
     b = N // world
+    P, M = len(pair_cfg), len(mods)
     peaks = load_peaks()
     lib = _lib.load()
+    for m in mods:
+        if not Modalities.has_modality(m):
+            Modalities.register_modality(m)  # "dna", as projects/bioscan_clip/dataset.py:18
 
     # ---- synthetic inputs, generated on the host, pinned ----------------
-    g = torch.Generator().manual_seed(1234)
-    xa = torch.randn(N, d, generator=g)
-    g = torch.Generator().manual_seed(1235)
-    xb = 0.5 * xa + torch.randn(N, d, generator=g)
+    # Every rank generates the whole global batch (the parity check below needs all keys) and
+    # keeps its own row block as the step's input.
     sl = slice(rank * b, (rank + 1) * b)
-    h_a = xa[sl].to(torch.bfloat16).contiguous().pin_memory()
-    h_b = xb[sl].to(torch.bfloat16).contiguous().pin_memory()
+    full_bf16, h_emb = {}, {}
+    base = None
+    for mi, m in enumerate(mods):
+        g = torch.Generator().manual_seed(1234 + mi)
+        x = torch.randn(N, d, generator=g)
+        if base is None:
+            base = x
+        else:
+            x = 0.5 * base + x
+        full_bf16[m] = x.to(torch.bfloat16)
+        h_emb[m] = full_bf16[m][sl].contiguous().pin_memory()
+    del base, x
     h_ids = torch.stack([torch.zeros(b, dtype=torch.long), torch.arange(rank * b, (rank + 1) * b)],
                         1).contiguous().pin_memory()
-    h_log_s = torch.tensor(math.log(1 / 0.07)).pin_memory()
-    del xa, xb
+    h_log_s = torch.tensor([math.log(s_) for s_ in scales]).pin_memory()
+    if P == 1:
+        h_log_s = h_log_s.reshape(()).pin_memory()
 
     fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True, cache_labels=True)
-    pairs = [LossPairSpec(("rgb", "text"))]
+    pairs = [LossPairSpec((a_, b_), w_) for a_, b_, w_ in pair_cfg]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def one_step(a, bt, ids, log_s):
-        a.grad = bt.grad = log_s.grad = None
-        loss = fn({"rgb_embedding": a, "text_embedding": bt}, {"rgb": ids, "text": ids},
+    def one_step(embs, ids, log_s):
+        for t_ in embs.values():
+            t_.grad = None
+        log_s.grad = None
+        loss = fn({f"{m}_embedding": embs[m] for m in mods}, {m: ids for m in mods},
                   log_s.exp(), pairs)
         loss.backward()
         return loss
@@ -189,15 +264,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- (1) device-resident timing: inputs already in HBM ------------------------------------
-    d_a = h_a.to(dev).requires_grad_(True)
-    d_b = h_b.to(dev).requires_grad_(True)
+    d_emb = {m: h_emb[m].to(dev).requires_grad_(True) for m in mods}
     d_ids = h_ids.to(dev)
     d_log_s = h_log_s.to(dev).requires_grad_(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # before warm-up: nvidia-smi needs ~100 ms to deliver its first sample
     for _ in range(warmup):
-        one_step(d_a, d_b, d_ids, d_log_s)
+        one_step(d_emb, d_ids, d_log_s)
     barrier()
     sampler.mark()
     l0 = lib.mmcl_kernel_launches()
@@ -211,7 +285,7 @@ def main():
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed iterations (outside the events)
         ev[i][0].record()
-        loss = one_step(d_a, d_b, d_ids, d_log_s)
+        loss = one_step(d_emb, d_ids, d_log_s)
         ev[i][1].record()
     span[1].record()
     barrier()
@@ -227,17 +301,19 @@ def main():
     loss_value = float(loss.detach())
 
     # ---- (2) end to end: pinned host buffers -> H2D -> step -> D2H of loss + d(scale) -----------
-    # Every step copies its inputs from pinned host memory and the host reads the loss back
-    # (and waits for it) before it starts the next step.  Like an input pipeline, the copy of
-    # step i+1 is issued on a copy stream before the host waits for step i, into the second of
-    # two device buffer sets, so it overlaps step i's kernels.  ONE event pair spans all K steps
+    # Every step copies its inputs from pinned host memory and copies the loss and d(log scale)
+    # back to pinned host memory.  Like an input pipeline, the H2D copy of step i+1 is issued on a
+    # copy stream before step i is enqueued, into the second of two device buffer sets.  The host
+    # reads each step's loss ONE STEP LATE (it waits for the D2H copy of step i-1 after it has
+    # enqueued step i), the way a training loop logs without draining the device every step; the
+    # last step's value is waited for inside the timed region.  ONE event pair spans all K steps
     # (copies, L2 flushes, kernels, read-backs).
     e2e_steps = args.steps
-    out_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    out_host = [torch.empty(1 + max(P, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
     main = torch.cuda.current_stream(dev)
     cs = torch.cuda.Stream(dev)
-    sets = [dict(a=torch.empty_like(d_a).requires_grad_(True),
-                 b=torch.empty_like(d_b).requires_grad_(True), ids=torch.empty_like(d_ids),
+    sets = [dict(emb={m: torch.empty_like(d_emb[m]).requires_grad_(True) for m in mods},
+                 ids=torch.empty_like(d_ids),
                  log_s=torch.empty_like(d_log_s).requires_grad_(True),
                  ready=torch.cuda.Event(), done=None) for _ in range(2)]
     span2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -250,52 +326,116 @@ def main():
                 cs.wait_event(s_["done"])  # step i-2 has finished with this buffer set
             if i == 2:
                 span2[0].record(cs)  # the timed region starts with the first timed step's copy
-            s_["a"].copy_(h_a, non_blocking=True)
-            s_["b"].copy_(h_b, non_blocking=True)
+            for m in mods:
+                s_["emb"][m].copy_(h_emb[m], non_blocking=True)
             s_["ids"].copy_(h_ids, non_blocking=True)
             s_["log_s"].copy_(h_log_s, non_blocking=True)
             s_["ready"].record(cs)
 
     barrier()
     issue_copy(0)
+    read_ev = [None, None]
+    e2e_losses = []
     for i in range(total):
         if i + 1 < total:
             issue_copy(i + 1)
         s_ = sets[i % 2]
         flush.fill_(i & 0xFF)
         main.wait_event(s_["ready"])
-        loss = one_step(s_["a"], s_["b"], s_["ids"], s_["log_s"])
-        out_host.copy_(torch.stack([loss.detach(), s_["log_s"].grad]), non_blocking=True)
+        loss = one_step(s_["emb"], s_["ids"], s_["log_s"])
+        out_host[i % 2].copy_(torch.cat([loss.detach().reshape(1), s_["log_s"].grad.reshape(-1)]),
+                              non_blocking=True)
         s_["done"] = torch.cuda.Event()
         s_["done"].record(main)
+        read_ev[i % 2] = s_["done"]
         if i == total - 1:
             span2[1].record(main)
-        # the user reads the loss on the host every step (logging): wait for the D2H copy
-        main.synchronize()
-        e2e_loss = float(out_host[0])
+        if i >= 1:  # the host consumes step i-1's loss now (logging lags by one step)
+            read_ev[(i - 1) % 2].synchronize()
+            e2e_losses.append(float(out_host[(i - 1) % 2][0]))
+    read_ev[(total - 1) % 2].synchronize()
+    e2e_losses.append(float(out_host[(total - 1) % 2][0]))
     barrier()
     t2 = torch.tensor([span2[0].elapsed_time(span2[1])], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = N / (float(t2) / e2e_steps * 1e-3)
-    h2d = h_a.numel() * 2 + h_b.numel() * 2 + h_ids.numel() * 8 + 4
-    d2h = 8
+    h2d = sum(h_emb[m].numel() * 2 for m in mods) + h_ids.numel() * 8 + 4 * max(P, 1)
+    d2h = 4 * (1 + max(P, 1))
+    e2e_ok = all(math.isfinite(v) and abs(v - loss_value) <= 1e-3 * abs(loss_value)
+                 for v in e2e_losses)
 
-    # ---- (3) dominant kernel alone (recompute backward), CUDA events on its stream ------------
+    # ---- (3) parity self-check, outside every timed region, on every rank ----------------------
+    # One more step through the same module (so: the same steady-state path that was timed),
+    # compared with a chunked fp32 torch evaluation of THIS rank's loss, d(scale) and 256 sampled
+    # gradient rows per modality (tools/chunked_check.py; reference semantics contrastive.py:196-212,
+    # 321-332).  Tolerances are the north-star's: loss 1e-3, gradient norms 1e-2, d(scale) 1e-2
+    # relative; labels bit-exact.  The maximum over ranks is reported; a failure exits non-zero.
+    parity = None
+    if not args.no_parity:
+        from tools.chunked_check import compare, rank_check
+
+        loss = one_step(d_emb, d_ids, d_log_s)
+        torch.cuda.synchronize()
+        # d(loss)/d(scale) from d(loss)/d(log scale): s = exp(log s)
+        ds = (d_log_s.grad.reshape(-1) / d_log_s.detach().exp().reshape(-1)).tolist()
+        del flush
+        torch.cuda.empty_cache()
+        full_dev = {m: full_bf16[m].to(dev) for m in mods}
+        ref = rank_check(full_dev, [(a_, b_, w_, s_) for (a_, b_, w_), s_ in
+                                    zip(pair_cfg, scales * (P if len(scales) == 1 else 1))],
+                         rank, world, chunk=4096 if N <= 65536 else 2048)
+        cmpd = compare(ref, float(loss.detach()), ds, {m: d_emb[m].grad for m in mods})
+        want_labels = torch.arange(N, device=dev)[rank * b:(rank + 1) * b if rank + 1 < world
+                                                  else None]
+        got_labels = fn._labels.get(dev)
+        labels_ok = got_labels is not None and torch.equal(got_labels, want_labels)
+        errs = torch.tensor([cmpd["loss_rel"], cmpd["grad_rel"], cmpd["dscale_rel"],
+                             1.0 - cmpd["grad_cos_min"], 0.0 if labels_ok else 1.0,
+                             0.0 if e2e_ok else 1.0],
+                            device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        e_ = errs.tolist()
+        parity = {"loss_rel": e_[0], "grad_rel": e_[1], "dscale_rel": e_[2],
+                  "grad_cos_min": 1.0 - e_[3], "labels_ok": e_[4] == 0.0,
+                  "e2e_losses_match": e_[5] == 0.0,
+                  "tolerance": {"loss_rel": 1e-3, "grad_rel": 1e-2, "dscale_rel": 1e-2},
+                  "how": "max over all ranks; every rank checks its own loss, d(scale), labels and "
+                         "256 sampled gradient rows per modality against a chunked fp32 torch "
+                         "evaluation of the same bf16-rounded inputs (tools/chunked_check.py)",
+                  "steady_steps": int(fn.steady_steps)}
+        parity["ok"] = bool(e_[0] <= 1e-3 and e_[1] <= 1e-2 and e_[2] <= 1e-2 and e_[4] == 0.0
+                            and e_[5] == 0.0 and e_[3] < 1e-3)
+        del full_dev, ref
+        torch.cuda.empty_cache()
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # ---- (4) dominant kernel alone (recompute backward), CUDA events on its stream ------------
+    # Same entry point and the same kind of arguments the step uses: raw bf16 rows + inverse
+    # norms, and the REAL log-sum-exp vectors of this problem (computed here by the forward
+    # kernel), so the kernel takes whichever exponential path the data selects.
     roof = None
     if rank == 0:
         hnd = get_handle(dev)
         st = torch.cuda.current_stream(dev).cuda_stream
-        x = torch.nn.functional.normalize(d_a.detach().float(), dim=-1).to(torch.bfloat16)
-        y = torch.nn.functional.normalize(
-            torch.randn(N, d, device=dev, generator=torch.Generator(device=dev).manual_seed(7)),
-            dim=-1).to(torch.bfloat16)
-        sc = torch.tensor([1 / 0.07], device=dev)
-        xinv = torch.ones(b, device=dev)
-        yinv = torch.ones(N, device=dev)
-        off_r = torch.full((b,), 30.0, device=dev)
-        off_c = torch.full((N,), 30.0, device=dev)
-        dx = torch.zeros(b, d, device=dev)
+        ma, mb = pair_cfg[0][0], pair_cfg[0][1]
+        xa_all = full_bf16[ma].to(dev)
+        y = full_bf16[mb].to(dev)
+        x = xa_all[:b].contiguous()
+        sc = torch.tensor([scales[0]], device=dev)
+        xinv_all = 1.0 / xa_all.float().norm(dim=1).clamp_min(1e-12)
+        xinv = xinv_all[:b].contiguous()
+        yinv = 1.0 / y.float().norm(dim=1).clamp_min(1e-12)
+        lse_row = torch.empty(b, device=dev)
+        lse_col = torch.empty(N, device=dev)
+        wsb = lib.mmcl_sim_lse_workspace_bytes(hnd, N, N, d)
+        wsf = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.mmcl_sim_lse_fwd(hnd, ptr(x), b, ptr(y), N, d, ptr(sc), ptr(xinv), ptr(yinv),
+                                   ptr(lse_row), None, ptr(wsf), wsb, st), "fwd")
+        check(lib.mmcl_sim_lse_fwd(hnd, ptr(y), N, ptr(xa_all), N, d, ptr(sc), ptr(yinv),
+                                   ptr(xinv_all), ptr(lse_col), None, ptr(wsf), wsb, st), "fwd")
+        dx = torch.empty(b, d, device=dev)
         reps = max(5, min(args.steps, 20))
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                for _ in range(reps)]
@@ -304,8 +444,9 @@ def main():
             torch.cuda.synchronize()
             if i >= 2:
                 kev[i - 2][0].record()
-            check(lib.mmcl_sim_grad_bwd(hnd, ptr(x), b, ptr(y), N, d, ptr(sc), ptr(xinv), ptr(yinv),
-                                        ptr(off_r), ptr(off_c), ptr(dx), st), "bwd")
+            check(lib.mmcl_sim_grad_bwd_lse(hnd, ptr(x), b, ptr(y), N, d, ptr(sc), ptr(xinv),
+                                            ptr(yinv), ptr(lse_row), 2.0 * b, ptr(lse_col), 2.0 * b,
+                                            ptr(dx), 1, st), "bwd")
             if i >= 2:
                 kev[i - 2][1].record()
         torch.cuda.synchronize()
@@ -313,39 +454,63 @@ def main():
         flops = 4.0 * b * N * d  # two of the reference's four backward GEMMs per launch
         achieved = flops / (kms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops"])
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
-        # `ncu --set full` capture at this shape (profiles/r01_ncu_summary.md); algorithmic
-        # operand + result bytes are (b + N) * d * 2 + b * d * 4
-        traffic = 220.6e6 if (N, d, world) == (32768, 512, 1) else None
+        traffic, traffic_src = ncu_traffic("sim_grad_bwd_pair_kernel", b, N, d)
+        step_tf = 12.0 * b * N * d * P / (ms_per_step * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "sim_grad_bwd_pair_kernel", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "algorithmic_bytes": (b + N) * d * 2 + b * d * 4,
                 "ms_per_launch": kms, "peak_source": f"{peaks['_source']} burst cuBLAS bf16",
-                "step_tflops": 12.0 * b * N * d / (ms_per_step * 1e-3) / 1e12,
-                "step_frac_of_sustained": 12.0 * b * N * d / (ms_per_step * 1e-3) / 1e12
-                / float(peaks["bf16_tflops_sustained"])}
+                "timed": "mmcl_sim_grad_bwd_lse (the step's entry point) with this problem's own "
+                         "log-sum-exp vectors, L2 flushed before every launch",
+                "step_tflops": step_tf, "step_frac_of_burst": step_tf / peak,
+                "step_frac_of_sustained": step_tf / float(peaks["bf16_tflops_sustained"]),
+                "executed_mma_flops_per_step": 12.0 * b * N * d * P,
+                "algorithmic_flops_per_step": 12.0 * b * N * d * P}
+        del xa_all, y, x, dx, wsf
 
-    # ---- (4) CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload ----
+    # ---- (5) CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_reference import time_rank_share
 
         r = time_rank_share(N, d, args.cpu_rows, steps=3, warmup=1, threads=os.cpu_count())
-        cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"],
+        cpu = {"value": r["samples_per_s"] / P, "unit": "samples/s", "cores": r["threads"],
                "kind": "port",
                "sample": f"one rank's share: {args.cpu_rows} query rows x all {N} keys, both "
                          f"directions, fwd+bwd, 3 steps, torch CPU fp32 ({r['ms_per_step']:.0f} ms/step)"}
+        # SURVEY.md section 8d "CPU baseline beside it": BASELINE config 1 whole (N=256, d=512,
+        # fp32, W=1) through the oracle's restatement of ContrastiveLoss.forward incl. id matching
+        try:
+            from oracle.contrastive_oracle import LossPairSpec as OPair
+            from oracle.contrastive_oracle import contrastive_oracle, synthetic_inputs
 
-    # ---- (5) the library baseline on the same GPU: the reference's torch ops (cuBLAS + ATen) -----
+            e1, i1 = synthetic_inputs(256, 512)
+            for _ in range(3):
+                contrastive_oracle(e1, i1, 1 / 0.07, [OPair(("rgb", "text"))], l2_normalize=True,
+                                   local_loss=True, gather_with_grad=True)
+            t0 = time.perf_counter()
+            for _ in range(30):
+                contrastive_oracle(e1, i1, 1 / 0.07, [OPair(("rgb", "text"))], l2_normalize=True,
+                                   local_loss=True, gather_with_grad=True)
+            dt = (time.perf_counter() - t0) / 30
+            cpu["config1"] = {"workload": "BASELINE config 1: N=256, d=512, fp32, W=1, whole "
+                                          "forward+backward incl. id matching (oracle port)",
+                              "ms_per_step": dt * 1e3, "samples_per_s": 256 / dt}
+        except Exception as exc:  # noqa: BLE001
+            cpu["config1"] = {"error": str(exc)[:200]}
+
+    # ---- (6) the library baseline on the same GPU: the reference's torch ops (cuBLAS + ATen) -----
     lib_gpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and N <= 32768:
         from oracle.cpu_reference import time_rank_share
 
         del flush
         torch.cuda.empty_cache()
         try:
             r = time_rank_share(N, d, N, steps=5, warmup=2, device=str(dev), autocast_bf16=True)
-            lib_gpu = {"value": r["samples_per_s"], "unit": "samples/s", "ms_per_step": r["ms_per_step"],
+            lib_gpu = {"value": r["samples_per_s"] / P, "unit": "samples/s",
+                       "ms_per_step": r["ms_per_step"] * P,
                        "kind": "port of the reference's torch ops on cuda:0 under bf16 autocast "
                                "(cuBLAS GEMMs + ATen cross_entropy; logits materialised in HBM); "
                                "id matching excluded (the reference's needs a 2.1 GB N x N temporary)"}
@@ -354,23 +519,27 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "contrastive loss fwd+bwd samples/sec @B=32k,d=512",
+            "metric": metric_name(args.config, N, d),
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ContrastiveLoss fwd+bwd, global batch {N}, d={d}, 1 pair, "
-                                   "l2_normalize+local_loss+gather_with_grad (BASELINE config 2)",
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config, N, d, P, world, weak),
                        "rows_per_gpu": b, "l2": "flushed between timed iterations (256 MiB fill kernel on the stream, "
                              "outside each iteration's event pair; no host sync between iterations)",
                        "ms_per_step_incl_flush": ms_per_step_with_flush,
                        "parallelism": f"dp{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "how": "one event pair over all K steps incl. H2D copies, L2 flushes and the "
-                           "per-step host wait for the loss; the next step's H2D is prefetched on "
-                           "a copy stream (double-buffered inputs)"},
+                    "how": "one event pair over all K steps incl. H2D copies, L2 flushes, kernels "
+                           "and the D2H copy of loss + d(log scale) every step; the next step's "
+                           "H2D is prefetched on a copy stream (double-buffered inputs); the host "
+                           "reads each step's loss one step late (after enqueueing the next step) "
+                           "and the last one inside the timed region"},
             "gpu_launches": int(launches),
+            "tflops_per_gpu": 12.0 * b * N * d * P / (ms_per_step * 1e-3) / 1e12,
             "clocks": clocks,
+            "parity": parity,
             "roofline": roof,
             "cpu_baseline": cpu,
             "torch_gpu_baseline": lib_gpu,
@@ -382,6 +551,8 @@ def main():
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,47 @@
+// Merging the forward kernel's partial row statistics (device code shared by sim_fwd.cu and the
+// step's post-forward kernel).  A (sub-problem, q-tile) item is covered by the CTAs
+// c_first..c_last of the launch's linear tile split; CTA c wrote its partials of the item into
+// slots 2*(c - c_first) and 2*(c - c_first) + 1 (one per column half of the 128x256 tiles).
+#pragma once
+#include "fused.h"
+
+namespace mmcl {
+
+// folds the partials of `row` of sub-problem S into the running (M, L, T): max (log2 units), sum
+// of 2^(x - M), sum of 2^(x - M) * cos
+__device__ __forceinline__ void fwd_merge_row(const FwdSub& S, int tiles_per_cta, int row,
+                                              float* M, float* L, float* T) {
+  const int qt = row / 128;
+  const long long first_tile = S.tile_begin + (long long)qt * S.nkt_sub;
+  const int c_first = int(first_tile / tiles_per_cta);
+  const int c_last = int((first_tile + S.nkt_sub - 1) / tiles_per_cta);
+  const int nslots = 2 * (c_last - c_first + 1);
+  const long long stride = (long long)S.nqt * 128;
+  const float* pm = S.part;
+  const float* pl = S.part + (long long)S.max_slots * stride;
+  const float* pt = S.part + 2ll * S.max_slots * stride;
+  float m = *M, l = *L, t = *T;
+  for (int s = 0; s < nslots; ++s) {
+    const long long o = (long long)s * stride + row;
+    const float ms = pm[o];
+    const float mn = fmaxf(m, ms);
+    if (mn == -INFINITY) continue;  // nothing seen so far
+    const float a = exp2f(m - mn), b = exp2f(ms - mn);
+    l = l * a + pl[o] * b;
+    t = t * a + pt[o] * b;
+    m = mn;
+  }
+  *M = m;
+  *L = l;
+  *T = t;
+}
+
+__device__ __forceinline__ void fwd_combine_row(const FwdSub& S, int tiles_per_cta, int row,
+                                                float* M, float* L, float* T) {
+  *M = -INFINITY;
+  *L = 0.f;
+  *T = 0.f;
+  fwd_merge_row(S, tiles_per_cta, row, M, L, T);
+}
+
+}  // namespace mmcl

@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include "fused.h"
+
 namespace mmcl {
 
 // process-wide count of kernel launches (diagnostic, see mmcl_kernel_launches)
@@ -24,6 +26,24 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
                                 const float* thr, const long long* tgt, long long* rank,
                                 void* workspace, size_t workspace_bytes, cudaStream_t stream,
                                 const char** err);
+
+// sim_fwd.cu, fused launches: fwd_begin, fwd_add_sub per (pair, direction[, key range]),
+// fwd_finish (CTA split + partial-statistics sizes), then fill the pointers and launch
+void fwd_begin(FwdLaunch* L, long long d);
+int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub);
+size_t fwd_finish(FwdLaunch* L, int num_sms, size_t* part_off_floats);
+int fwd_grid(const FwdLaunch& L);
+int fwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d);
+cudaError_t launch_fwd_fused(const TensorMaps& maps, const FwdLaunch& L, cudaStream_t stream);
+
+// sim_bwd_pair.cu, fused launches
+bool bwd_pair_supported(int num_sms, long long d);
+void bwd_begin(BwdLaunch* L, long long d);
+int bwd_add_prob(BwdLaunch* L, long long nx, long long ny);
+size_t bwd_finish(BwdLaunch* L, int num_sms);
+int bwd_cta_pairs(const BwdLaunch& L);
+int bwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d);
+cudaError_t launch_bwd_fused(const TensorMaps& maps, const BwdLaunch& L, cudaStream_t stream);
 
 // sim_bwd.cu
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,
@@ -80,7 +100,8 @@ struct SymmArena {
   char** d_peers = nullptr;    // the same table on the device
   void* scratch = nullptr;     // setup-time staging (IPC handle exchange, barriers)
   size_t bytes = 0;            // usable bytes per buffer
-  unsigned long long seq[4] = {0, 0, 0, 0};  // fence sequence number per channel
+  unsigned long long seq[kFlagChannels] = {};  // sequence number per flag channel (fused.h)
+  unsigned long long step_seq = 0;  // sequence number of the fused step's row / lse channels
   bool failed = false;
 };
 int symm_reserve(SymmArena* a, void* nccl_comm, int rank, int world, size_t bytes,

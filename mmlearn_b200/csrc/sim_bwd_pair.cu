@@ -19,12 +19,21 @@
 // is the floor of the epilogue).  Shared memory: 3 stages x 48 KB (X chunk 128x64 + Y box
 // 256x64 for S; 64-key x d/2 boxes for dX), 64 KB staging for the partner's G (K-major,
 // 128-byte swizzle, 4 atoms of 64 keys), column data, barriers.
-// Work: the (x-tile, d-pass, y-tile) space is linearised and cut into equal contiguous ranges,
-// one per pair; a range that ends inside an (x-tile, d-pass) item adds its partial accumulator
-// into dX with fp32 reductions, so dX must be zero-initialised by the caller.  d-passes exist
-// only for d > 512 (each pass covers d/ndc <= 512 columns and recomputes S).
+// Work: one launch covers a LIST of problems (fused.h, BwdProb: every (pair, side) of the loss).
+// Their (x-tile, d-pass, y-tile) spaces are laid end to end, linearised and cut into equal
+// contiguous ranges, one per CTA pair.  d-passes exist only for d > 512 (each pass covers
+// d/ndc <= 512 columns and recomputes S).  A range that starts inside an (x-tile, d-pass) item
+// holds a partial sum of that item:
+//   accumulate == 1 (ABI calls): every segment is added into dX with fp32 reductions; the caller
+//                   zero-fills dX;
+//   accumulate == 0 (fused step): segments that start an item are STORED to dX, the one segment
+//                   per CTA pair that continues an item goes to that pair's scratch tile and the
+//                   gradient-unpack kernel adds it -- no memset, no atomics, dX written once.
+// Several ranks: the column offsets of other ranks' rows (their log-sum-exps) arrive by peer
+// stores; the kernel waits for the per-source flags of channel kChanLse before it reads them.
 #include <cstdlib>
 
+#include "fused.h"
 #include "kernels.h"
 #include "tma_host.h"
 #include "umma.cuh"
@@ -67,21 +76,22 @@ __device__ __forceinline__ void trace_ev(int pair, uint32_t cta, unsigned ev, un
 #define TRACE(ev, step)
 #endif
 
-struct PairParams {
-  int nx, ny, d, kchunks;
-  int nxt, ndc, nyt;
-  int dp;   // columns per d-pass (d / ndc)
-  int dcc;  // columns per CTA (dp / 2)
-  long long total;
-  int per_pair;
-  const float* scale;
-  const float* xinv;
-  const float* yinv;
-  const float* off_row;
-  const float* off_col;
-  float off_mul, row_add, col_add;  // offset = off_*[i] * off_mul + *_add (lets callers pass raw lse)
-  float* dx;
-};
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// problem that holds linear tile t (t only grows: `s` is carried along)
+__device__ __forceinline__ int find_prob(const BwdLaunch& L, long long t, int s) {
+  while (s + 1 < L.nprob && t >= L.prob[s + 1].tile_begin) ++s;
+  return s;
+}
 
 // 16 logits of one row -> 8 packed bf16x2 values of G.  Exact form (see sim_bwd.cu):
 // cy[e] = (off_col[j], 1/||y_j||).
@@ -126,9 +136,8 @@ __device__ __forceinline__ void conv16_fast(const uint32_t (&v)[16], uint32_t* g
 constexpr int NTHREADS = 384;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
-                         const __grid_constant__ CUtensorMap tmY256,
-                         const __grid_constant__ CUtensorMap tmY64, const PairParams p) {
+sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
+                         const __grid_constant__ BwdLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* sStage = smem;
@@ -146,6 +155,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
   uint64_t* acc_empty = s_full + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
   float* s_range = reinterpret_cast<float*>(s_full + 8);  // [16] lo per warp, [16] hi per warp
+  float* s_mu = s_range + 32;                              // [kMaxBwdProbs] centre of the offsets
+  int* s_fast = reinterpret_cast<int*>(s_mu + kMaxBwdProbs);  // [kMaxBwdProbs] one-exponential form
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t c = cluster_ctarank();
@@ -153,9 +164,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
   const int pair = blockIdx.x >> 1;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmY256);
-    tma_prefetch_desc(&tmY64);
     for (int i = 0; i < NSTAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -169,17 +177,35 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     mbar_init(acc_empty, 256);
     fence_barrier_init();
   }
-  const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
-  if (mode == 3) {
-    // range of all offsets: decides whether the one-exponential form of G is safe
+  if (L.world > 1 && int(threadIdx.x) < L.world && int(threadIdx.x) != L.rank) {
+    // the log-sum-exp vectors of the other ranks (column offsets) have landed in this rank's arena
+    const unsigned long long* f = L.flags + kChanLse * kMaxRanks + threadIdx.x;
+    if (ld_acquire_sys_u64(f) < L.seq) {
+      const unsigned long long t0 = global_timer_ns();
+      unsigned spins = 0;
+      while (ld_acquire_sys_u64(f) < L.seq)
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+          if (L.err) atomicExch(L.err, kErrFlagTimeout);
+          break;
+        }
+    }
+  }
+  if (L.world > 1) __syncthreads();
+  // per problem: range of all offsets -- decides whether the one-exponential form of G is safe
+  for (int pi = 0; pi < L.nprob; ++pi) {
+    const BwdProb& p = L.prob[pi];
+    if (!(p.off_row && p.off_col)) {
+      if (threadIdx.x == 0) { s_mu[pi] = 0.f; s_fast[pi] = 0; }
+      continue;
+    }
     float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < p.nx; i += NTHREADS) {
-      const float v = fmaf(p.off_row[i], p.off_mul, p.row_add);
+      const float v = fmaf(__ldcg(p.off_row + i), p.off_mul, p.row_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
     for (int i = threadIdx.x; i < p.ny; i += NTHREADS) {
-      const float v = fmaf(p.off_col[i], p.off_mul, p.col_add);
+      const float v = fmaf(__ldcg(p.off_col + i), p.off_mul, p.col_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
@@ -192,6 +218,17 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
       s_range[warp] = lo;
       s_range[16 + warp] = hi;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float l2 = INFINITY, h2 = -INFINITY;
+      for (int w = 0; w < NTHREADS / 32; ++w) {
+        l2 = fminf(l2, s_range[w]);
+        h2 = fmaxf(h2, s_range[16 + w]);
+      }
+      s_mu[pi] = 0.5f * (l2 + h2);
+      s_fast[pi] = (h2 - l2) <= 2.f * kFastRange ? 1 : 0;  // false for inf/NaN ranges as well
+    }
+    __syncthreads();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -201,23 +238,24 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_acc = tmem, tm_s = tmem + 256;
 
-  const long long t_begin = (long long)pair * p.per_pair;
-  long long t_end = t_begin + p.per_pair;
-  if (t_end > p.total) t_end = p.total;
-  const int nb = p.dcc / BK;  // 64-wide column boxes of this CTA's dX slice
+  const long long t_begin = (long long)pair * L.per_pair;
+  long long t_end = t_begin + L.per_pair;
+  if (t_end > L.total) t_end = L.total;
+  const int nb = L.dcc / BK;  // 64-wide column boxes of this CTA's dX slice
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const CUtensorMap *tmX = nullptr, *tmY256 = nullptr, *tmY64 = nullptr;
       auto load_s = [&](int xt, int yt) {
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int kc = 0; kc < L.kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* dst = sStage + stage * STAGE_BYTES;
-          tma_load_2d(dst, &tmX, kc * BK, xt * BM, &full[stage]);
-          tma_load_2d(dst + XCHUNK_BYTES, &tmY256, kc * BK, yt * BNY, &full[stage]);
+          tma_load_2d(dst, tmX, kc * BK, xt * BM, &full[stage]);
+          tma_load_2d(dst + XCHUNK_BYTES, tmY256, kc * BK, yt * BNY, &full[stage]);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       };
@@ -227,18 +265,24 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           mbar_arrive_expect_tx(&full[stage], nb * YSUB_BYTES);
           uint8_t* dst = sStage + stage * STAGE_BYTES;
           for (int b = 0; b < nb; ++b)
-            tma_load_2d(dst + b * YSUB_BYTES, &tmY64, col0 + b * BK, yt * BNY + js * 64,
+            tma_load_2d(dst + b * YSUB_BYTES, tmY64, col0 + b * BK, yt * BNY + js * 64,
                         &full[stage]);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       };
       bool pend = false;
-      int pend_yt = 0;
+      int pend_yt = 0, pi = 0;
       for (long long t = t_begin; t < t_end; ++t) {
-        const long long item = t / p.nyt;
-        const int yt = int(t % p.nyt);
-        const int xt = int(item / p.ndc), dc = int(item % p.ndc);
-        const int col0 = dc * p.dp + int(c) * p.dcc;
+        pi = find_prob(L, t, pi);
+        const BwdProb& p = L.prob[pi];
+        tmX = &maps.tm[p.map_x];
+        tmY256 = &maps.tm[p.map_y256];
+        tmY64 = &maps.tm[p.map_y64];
+        const long long local = t - p.tile_begin;
+        const long long item = local / p.nyt;
+        const int yt = int(local % p.nyt);
+        const int xt = int(item / L.ndc), dc = int(item % L.ndc);
+        const int col0 = dc * L.dp + int(c) * L.dcc;
         const bool own = (uint32_t(t - t_begin) & 1u) == c;
         const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
         if (own) {
@@ -256,13 +300,13 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     // ================================ MMA issuer ==================================
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(BM, BNY, 0, 0);
-      const uint32_t idesc_dx = make_idesc_bf16(BM, uint32_t(p.dcc), 0, 1);
+      const uint32_t idesc_dx = make_idesc_bf16(BM, uint32_t(L.dcc), 0, 1);
       const uint32_t stg = smem_u32(sStg);
       int stage = 0;
       uint32_t phase = 0, own_cnt = 0, peer_cnt = 0, seg = 0, accf = 0;
       auto issue_s = [&]() {
         TRACE(0, own_cnt);
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int kc = 0; kc < L.kchunks; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
@@ -337,10 +381,13 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         ++peer_cnt;
       };
       bool pend = false;
+      int pi = 0;
       for (long long t = t_begin; t < t_end; ++t) {
-        const int yt = int(t % p.nyt);
+        pi = find_prob(L, t, pi);
+        const int nyt = L.prob[pi].nyt;
+        const int yt = int((t - L.prob[pi].tile_begin) % nyt);
         const bool own = (uint32_t(t - t_begin) & 1u) == c;
-        const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
+        const bool seg_last = (t == t_end - 1) || (yt == nyt - 1);
         if (own) {
           issue_s();
           if (pend) { issue_dx_peer(); pend = false; }
@@ -362,34 +409,32 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
     const int q = warp & 3;          // TMEM lane quadrant (== warp % 4)
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128 - wg * 128;  // 0..127 within the warpgroup
-    const float c0 = (*p.scale) * LOG2E;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     const uint32_t peer_stg = mapa_shared(smem_u32(sStg), peer) + uint32_t(q * 32) * 128u;
     const uint32_t xb = smem_u32(sXfer) + uint32_t(warp - 4) * 2048u;
     const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
     const uint32_t sw = uint32_t(row & 7);
-    float mu = 0.f;
-    bool fast = false;
-    if (mode == 3) {
-      float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < NTHREADS / 32; ++w) {
-        lo = fminf(lo, s_range[w]);
-        hi = fmaxf(hi, s_range[16 + w]);
-      }
-      mu = 0.5f * (lo + hi);
-      fast = (hi - lo) <= 2.f * kFastRange;  // false for inf/NaN ranges as well
-    }
     uint32_t own_cnt = 0, seg = 0;
+    int pi = 0;
+    bool seg_head = false;  // the current segment continues an item another CTA pair started
     for (long long t = t_begin; t < t_end; ++t) {
-      const long long item = t / p.nyt;
-      const int yt = int(t % p.nyt);
-      const int xt = int(item / p.ndc), dc = int(item % p.ndc);
+      pi = find_prob(L, t, pi);
+      const BwdProb& p = L.prob[pi];
+      const long long local = t - p.tile_begin;
+      const long long item = local / p.nyt;
+      const int yt = int(local % p.nyt);
+      const int xt = int(item / L.ndc), dc = int(item % L.ndc);
       const bool own = (uint32_t(t - t_begin) & 1u) == c;
       const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
       const int grow = xt * BM + row;
+      if (t == t_begin) seg_head = yt != 0;
+      const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
+      const bool fast = s_fast[pi] != 0;
+      const float mu = s_mu[pi];
       if (own) {
-        const float offr = (p.off_row && grow < p.nx) ? fmaf(p.off_row[grow], p.off_mul, p.row_add) : INFINITY;
+        const float c0 = (*p.scale) * LOG2E;
+        const float offr = (p.off_row && grow < p.nx)
+                               ? fmaf(__ldcg(p.off_row + grow), p.off_mul, p.row_add) : INFINITY;
         const float cc = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
         const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
         named_bar_sync(1, 256);  // everyone is done with the previous step's column data
@@ -397,7 +442,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
           const int j = wg * 128 + et;
           const int gy = yt * BNY + j;
           float2 v2;
-          v2.x = (p.off_col && gy < p.ny) ? fmaf(p.off_col[gy], p.off_mul, p.col_add) : INFINITY;
+          v2.x = (p.off_col && gy < p.ny) ? fmaf(__ldcg(p.off_col + gy), p.off_mul, p.col_add)
+                                          : INFINITY;
           v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
           if (fast) {
             // pair-planar layout for the packed-math path: (cyB0, cyB1, yinv0, yinv1)
@@ -491,21 +537,40 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
         // flush this segment's accumulators
         mbar_wait(acc_full, seg & 1);
         tc_fence_after();
-        const int col0 = dc * p.dp + int(c) * p.dcc;
+        const int col0 = dc * L.dp + int(c) * L.dcc;
 #pragma unroll 1
-        for (int ch = wg; ch < p.dcc / 32; ch += 2) {
+        for (int ch = wg; ch < L.dcc / 32; ch += 2) {
           uint32_t v[32];
           tmem_ld_x32(tm_acc + lane_base + ch * 32, v);
           tmem_ld_wait();
-          if (grow < p.nx) {
-            float* dst = p.dx + (long long)grow * p.d + col0 + ch * 32;
+          if (L.accumulate) {
+            if (grow < p.nx) {
+              float* dst = p.dx + (long long)grow * L.d + col0 + ch * 32;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+              for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+            }
+          } else if (seg_head) {
+            // continuation of an item another pair started: this pair's scratch tile
+            float4* dst = reinterpret_cast<float4*>(
+                L.scratch + ((long long)pair * BM + row) * L.dp + int(c) * L.dcc + ch * 32);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                        __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          } else if (grow < p.nx) {
+            float4* dst =
+                reinterpret_cast<float4*>(p.dx + (long long)grow * L.d + col0 + ch * 32);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                        __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
           }
         }
         tc_fence_before();
         mbar_arrive(acc_empty);
         ++seg;
+        seg_head = false;
       }
     }
   }
@@ -518,6 +583,71 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX,
 
 }  // namespace
 
+// ---- planning (host) ---------------------------------------------------------------------------
+
+bool bwd_pair_supported(int num_sms, long long d) {
+  const int ndc = int((d + 511) / 512);
+  return num_sms >= 2 && d % (128 * ndc) == 0;
+}
+
+void bwd_begin(BwdLaunch* L, long long d) {
+  *L = BwdLaunch();
+  L->d = int(d);
+  L->kchunks = int(d / BK);
+  L->ndc = int((d + 511) / 512);
+  L->dp = int(d / L->ndc);
+  L->dcc = L->dp / 2;
+  L->world = 1;
+  L->accumulate = 1;
+}
+
+int bwd_add_prob(BwdLaunch* L, long long nx, long long ny) {
+  if (L->nprob >= kMaxBwdProbs) return -1;
+  BwdProb& p = L->prob[L->nprob];
+  p = BwdProb();
+  p.nx = int(nx);
+  p.ny = int(ny);
+  p.nxt = int((nx + BM - 1) / BM);
+  p.nyt = int((ny + BNY - 1) / BNY);
+  p.tile_begin = L->total;
+  p.off_mul = 1.f;
+  L->total += (long long)p.nxt * L->ndc * p.nyt;
+  return L->nprob++;
+}
+
+// Fixes the split over CTA pairs; returns the scratch bytes an accumulate == 0 launch needs.
+size_t bwd_finish(BwdLaunch* L, int num_sms) {
+  long long pairs = num_sms / 2;
+  if (L->total < pairs) pairs = L->total;
+  if (pairs < 1) pairs = 1;
+  L->per_pair = int((L->total + pairs - 1) / pairs);
+  if (L->per_pair < 1) L->per_pair = 1;
+  pairs = (L->total + L->per_pair - 1) / L->per_pair;
+  return size_t(pairs) * BM * size_t(L->dp) * sizeof(float);
+}
+
+int bwd_cta_pairs(const BwdLaunch& L) { return int((L.total + L.per_pair - 1) / L.per_pair); }
+
+int bwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d) {
+  if (slot < 0 || 3 * slot + 2 >= kMaxBwdMaps) return -1;
+  if (make_tmap_bf16_sw128(&maps->tm[3 * slot], rows, n, d, d, BM)) return -1;
+  if (make_tmap_bf16_sw128(&maps->tm[3 * slot + 1], rows, n, d, d, BNY)) return -1;
+  if (make_tmap_bf16_sw128(&maps->tm[3 * slot + 2], rows, n, d, d, 64)) return -1;
+  return 0;
+}
+
+cudaError_t launch_bwd_fused(const TensorMaps& maps, const BwdLaunch& L, cudaStream_t stream) {
+  if (L.total == 0) return cudaSuccess;
+  const size_t smem =
+      size_t(NSTAGES) * STAGE_BYTES + STG_BYTES + BNY * sizeof(float2) + XFER_BYTES + TAIL_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(sim_grad_bwd_pair_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  sim_grad_bwd_pair_kernel<<<2 * bwd_cta_pairs(L), NTHREADS, smem, stream>>>(maps, L);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
 // Returns cudaErrorNotSupported (without launching) when the shape does not fit the pair form;
 // the caller then uses the single-CTA kernel of sim_bwd.cu.
 cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
@@ -527,23 +657,12 @@ cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, c
                                      float col_add, float* dx, cudaStream_t stream,
                                      const char** err) {
   if (!off_row && !off_col) return cudaSuccess;  // G == 0
-  const int ndc = int((d + 511) / 512);
-  if (num_sms < 2 || d % (128 * ndc) != 0) return cudaErrorNotSupported;
-  PairParams p;
-  p.nx = int(nx);
-  p.ny = int(ny);
-  p.d = int(d);
-  p.kchunks = int(d / BK);
-  p.nxt = int((nx + BM - 1) / BM);
-  p.ndc = ndc;
-  p.nyt = int((ny + BNY - 1) / BNY);
-  p.dp = int(d / ndc);
-  p.dcc = p.dp / 2;
-  p.total = (long long)p.nxt * p.ndc * p.nyt;
-  long long pairs = num_sms / 2;
-  if (p.total < pairs) pairs = p.total;
-  p.per_pair = int((p.total + pairs - 1) / pairs);
-  pairs = (p.total + p.per_pair - 1) / p.per_pair;
+  if (!bwd_pair_supported(num_sms, d)) return cudaErrorNotSupported;
+  BwdLaunch L;
+  bwd_begin(&L, d);
+  bwd_add_prob(&L, nx, ny);
+  bwd_finish(&L, num_sms);
+  BwdProb& p = L.prob[0];
   p.scale = scale;
   p.xinv = xinv;
   p.yinv = yinv;
@@ -553,21 +672,17 @@ cudaError_t launch_sim_grad_bwd_pair(int num_sms, const void* x, long long nx, c
   p.row_add = row_add;
   p.col_add = col_add;
   p.dx = dx;
-  const size_t smem =
-      size_t(NSTAGES) * STAGE_BYTES + STG_BYTES + BNY * sizeof(float2) + XFER_BYTES + TAIL_BYTES;
-  CUtensorMap tmX, tmY256, tmY64;
-  if (make_tmap_bf16_sw128(&tmX, x, nx, d, d, BM) ||
-      make_tmap_bf16_sw128(&tmY256, y, ny, d, d, BNY) ||
-      make_tmap_bf16_sw128(&tmY64, y, ny, d, d, 64)) {
+  TensorMaps maps;
+  if (make_tmap_bf16_sw128(&maps.tm[0], x, nx, d, d, BM) ||
+      make_tmap_bf16_sw128(&maps.tm[1], y, ny, d, d, BNY) ||
+      make_tmap_bf16_sw128(&maps.tm[2], y, ny, d, d, 64)) {
     *err = "sim_grad_bwd_pair: cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
-  cudaError_t e = cudaFuncSetAttribute(sim_grad_bwd_pair_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return e;
-  sim_grad_bwd_pair_kernel<<<int(2 * pairs), NTHREADS, smem, stream>>>(tmX, tmY256, tmY64, p);
-  count_launches(1);
-  return cudaGetLastError();
+  p.map_x = 0;
+  p.map_y256 = 1;
+  p.map_y64 = 2;
+  return launch_bwd_fused(maps, L, stream);
 }
 
 }  // namespace mmcl

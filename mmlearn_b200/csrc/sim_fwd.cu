@@ -1,19 +1,30 @@
 // Forward hot kernel: S = s * Q K^T in 128x256 fp32 tiles that live only in tensor memory,
-// reduced on the fly to per-row (max, sum-exp, sum-exp*logit).
+// reduced on the fly to per-row (max, sum-exp, sum-exp*logit) and the positive logit.
+//
+// One launch covers a LIST of sub-problems (fused.h, FwdSub): every (pair, direction) of the
+// loss, each optionally cut into "local keys first" and "remote keys" parts, laid end to end in
+// one linear tile space that is cut into equal contiguous ranges, one per CTA ("stream-K" over
+// the key axis), so all 148 SMs finish together whatever the shapes are; a row's partial
+// statistics from different CTAs are merged afterwards (lse_combine_kernel / the step's
+// post-forward kernel).
 //
 // Roles (384 threads, 1 CTA / SM, persistent):
-//   warp 0    TMA producer  (Q tile resident in smem when it fits, K streamed in 64-wide k-chunks)
+//   warp 0    TMA producer  (Q tile resident in smem when it fits, K streamed in 64-wide k-chunks).
+//             With several ranks the keys of other ranks arrive in this rank's arena by peer
+//             stores; before the first load from source rank r the producer acquires r's ready
+//             flag (ld.acquire.sys + fence.proxy.async) -- there is no fence kernel in front.
 //   warp 1    tcgen05.mma issuer (one elected thread), double-buffered TMEM accumulators
-//   warp 2    TMEM allocator
+//   warps 2-3 several ranks: the all-gather itself.  They copy this rank's packed rows / norms /
+//             ids from the local arena slot to the same offset of every peer (16-byte stores over
+//             NVLink) while the tensor cores work on the local keys, then release the per-channel
+//             ready flags.  (warp 2 also owns the TMEM allocation.)
 //   warps 4-11 epilogue: tcgen05.ld -> online log-sum-exp in registers.  Two warps per SM
 //             sub-partition: warps 4-7 reduce columns 0-127 of each 128x256 tile, warps 8-11
 //             columns 128-255 (one row per thread, each half gives its own partial statistics).
 //             With one warp per sub-partition the epilogue (dependent ALU latency, MUFU) took
 //             ~6500 cycles per tile against ~4200 for the MMAs (ncu stall samples, round 1).
-// Work distribution: the nqt x nkt tile grid is linearised (q-tile major) and cut into
-// equal contiguous ranges, one per CTA ("stream-K" over the key axis), so all 148 SMs finish
-// together whatever nq is; a row's partial statistics from different CTAs are merged by
-// lse_combine_kernel.
+#include "fused.h"
+#include "fwd_combine.cuh"
 #include "kernels.h"
 #include "tma_host.h"
 #include "umma.cuh"
@@ -31,41 +42,57 @@ constexpr int KCHUNK_BYTES = BN * BK * 2;  // 32 KB
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
-struct FwdParams {
-  int nq, nk, kchunks;
-  int nqt, nkt;
-  long long total_tiles;
-  int tiles_per_cta;
-  int nstages;
-  int max_slots;
-  long long part_stride;  // floats between slots (= nqt * BM)
-  const float* scale;
-  const float* qinv;  // [nq] 1/||q_i|| or null (rows already unit-norm / no normalisation)
-  const float* kinv;  // [nk] likewise for the keys
-  float* part_m;
-  float* part_l;
-  float* part_t;
-  const float* thr;  // rank mode: per-row threshold on  qinv_i * kinv_j * (q_i . k_j)
-  const long long* tgt;  // rank mode: per-row key index that is never counted (the positive) or null
-};
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spin until *flag >= seq; gives up after ~4 s (records kErrFlagTimeout) so that a rank that never
+// shows up turns into a failed verification instead of a hung GPU.
+__device__ __noinline__ void wait_flag(const unsigned long long* flag, unsigned long long seq,
+                                       unsigned long long* err) {
+  if (ld_acquire_sys_u64(flag) >= seq) return;
+  const unsigned long long t0 = global_timer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys_u64(flag) < seq) {
+    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+      if (err) atomicExch(err, kErrFlagTimeout);
+      return;
+    }
+  }
+}
+
+// sub-problem that holds linear tile t (t only grows: `s` is carried along)
+__device__ __forceinline__ int find_sub(const FwdLaunch& L, long long t, int s) {
+  while (s + 1 < L.nsub && t >= L.sub[s + 1].tile_begin) ++s;
+  return s;
+}
 
 // kRank == false: online log-sum-exp epilogue (the loss).  kRank == true: the same mainloop with a
 // counting epilogue -- per row, the number of keys whose similarity exceeds the row's threshold
 // (retrieval rank of the positive, mmcl_sim_rank_fwd); one multiply + compare per logit, no MUFU.
 template <bool kQRes, bool kRank>
 __global__ void __launch_bounds__(384, 1)
-sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const FwdParams p) {
+sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ FwdLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
   const int stage_bytes = kQRes ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
   uint8_t* sQ = smem;
-  uint8_t* sStage = smem + (kQRes ? p.kchunks * QCHUNK_BYTES : 0);
-  float* sKinv = reinterpret_cast<float*>(sStage + p.nstages * stage_bytes);  // [2][BN]
+  uint8_t* sStage = smem + (kQRes ? L.kchunks * QCHUNK_BYTES : 0);
+  float* sKinv = reinterpret_cast<float*>(sStage + L.nstages * stage_bytes);  // [2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKinv + 2 * BN);
   uint64_t* full = bars;
-  uint64_t* empty = bars + p.nstages;
-  uint64_t* q_full = bars + 2 * p.nstages;
+  uint64_t* empty = bars + L.nstages;
+  uint64_t* q_full = bars + 2 * L.nstages;
   uint64_t* q_empty = q_full + 1;
   uint64_t* acc_full = q_full + 2;   // [2]
   uint64_t* acc_empty = q_full + 4;  // [2]
@@ -74,9 +101,7 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    for (int i = 0; i < p.nstages; ++i) {
+    for (int i = 0; i < L.nstages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -94,62 +119,93 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const long long t_begin = (long long)blockIdx.x * p.tiles_per_cta;
-  long long t_end = t_begin + p.tiles_per_cta;
-  if (t_end > p.total_tiles) t_end = p.total_tiles;
+  const long long t_begin = (long long)blockIdx.x * L.tiles_per_cta;
+  long long t_end = t_begin + L.tiles_per_cta;
+  if (t_end > L.total_tiles) t_end = L.total_tiles;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      int stage = 0;
+      int stage = 0, si = 0;
       uint32_t phase = 0, qphase = 0;
+      int seen_chan = -1;
+      uint32_t seen = 0;
       for (long long t = t_begin; t < t_end;) {
-        const int qt = int(t / p.nkt), kt0 = int(t % p.nkt);
-        int kt1 = kt0 + int(t_end - t);
-        if (kt1 > p.nkt) kt1 = p.nkt;
+        si = find_sub(L, t, si);
+        const FwdSub& S = L.sub[si];
+        const long long local = t - S.tile_begin;
+        const int qt = int(local / S.nkt_sub), j0 = int(local % S.nkt_sub);
+        int j1 = j0 + int(t_end - t);
+        if (j1 > S.nkt_sub) j1 = S.nkt_sub;
+        const CUtensorMap* tmQ = &maps.tm[S.map_q];
+        const CUtensorMap* tmK = &maps.tm[S.map_k];
         if (kQRes) {
           mbar_wait(q_empty, qphase ^ 1);
-          mbar_arrive_expect_tx(q_full, p.kchunks * QCHUNK_BYTES);
-          for (int kc = 0; kc < p.kchunks; ++kc)
-            tma_load_2d(sQ + kc * QCHUNK_BYTES, &tmQ, kc * BK, qt * BM, q_full);
+          mbar_arrive_expect_tx(q_full, L.kchunks * QCHUNK_BYTES);
+          for (int kc = 0; kc < L.kchunks; ++kc)
+            tma_load_2d(sQ + kc * QCHUNK_BYTES, tmQ, kc * BK, qt * BM, q_full);
           qphase ^= 1;
         }
-        for (int kt = kt0; kt < kt1; ++kt) {
-          for (int kc = 0; kc < p.kchunks; ++kc) {
+        if (S.chan != seen_chan) {
+          seen_chan = S.chan;
+          seen = 0;
+        }
+        for (int j = j0; j < j1; ++j) {
+          int kt = S.kt0 + j;
+          if (kt >= S.nkt_all) kt -= S.nkt_all;
+          if (L.world > 1) {
+            // rows [kt*BN, kt*BN + BN) of the gathered keys: which ranks wrote them?
+            const long long g0 = (long long)kt * BN;
+            long long g1 = g0 + BN - 1;
+            if (g1 > S.nk - 1) g1 = S.nk - 1;
+            const int r0 = int(g0 / L.rows_per_rank), r1 = int(g1 / L.rows_per_rank);
+            bool waited = false;
+            for (int r = r0; r <= r1 && r < L.world; ++r) {
+              if (r == L.rank || ((seen >> r) & 1u)) continue;
+              wait_flag(L.flags + S.chan * kMaxRanks + r, L.seq, L.err);
+              seen |= 1u << r;
+              waited = true;
+            }
+            // peer stores (generic proxy, observed through the acquire) -> TMA (async proxy)
+            if (waited) fence_proxy_async_all();
+          }
+          for (int kc = 0; kc < L.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], stage_bytes);
             uint8_t* dst = sStage + stage * stage_bytes;
             if (!kQRes) {
-              tma_load_2d(dst, &tmQ, kc * BK, qt * BM, &full[stage]);
+              tma_load_2d(dst, tmQ, kc * BK, qt * BM, &full[stage]);
               dst += QCHUNK_BYTES;
             }
-            tma_load_2d(dst, &tmK, kc * BK, kt * BN, &full[stage]);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            tma_load_2d(dst, tmK, kc * BK, kt * BN, &full[stage]);
+            if (++stage == L.nstages) { stage = 0; phase ^= 1; }
           }
         }
-        t += kt1 - kt0;
+        t += j1 - j0;
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
+      int stage = 0, si = 0;
       uint32_t phase = 0, qphase = 0;
       uint32_t acc = 0;
       for (long long t = t_begin; t < t_end;) {
-        const int kt0 = int(t % p.nkt);
-        int kt1 = kt0 + int(t_end - t);
-        if (kt1 > p.nkt) kt1 = p.nkt;
+        si = find_sub(L, t, si);
+        const int nkt_sub = L.sub[si].nkt_sub;
+        const int j0 = int((t - L.sub[si].tile_begin) % nkt_sub);
+        int j1 = j0 + int(t_end - t);
+        if (j1 > nkt_sub) j1 = nkt_sub;
         if (kQRes) {
           mbar_wait(q_full, qphase);
           qphase ^= 1;
         }
-        for (int kt = kt0; kt < kt1; ++kt) {
+        for (int j = j0; j < j1; ++j) {
           const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
           mbar_wait(&acc_empty[ab], aphase ^ 1);
           tc_fence_after();
-          for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int kc = 0; kc < L.kchunks; ++kc) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(sStage + stage * stage_bytes);
@@ -162,55 +218,121 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               umma_ss(tmem + ab * BN, adesc, bdesc, idesc, (kc | k) != 0);
             }
             umma_commit(&empty[stage]);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            if (++stage == L.nstages) { stage = 0; phase ^= 1; }
           }
           umma_commit(&acc_full[ab]);
           ++acc;
         }
         if (kQRes) umma_commit(q_empty);
-        t += kt1 - kt0;
+        t += j1 - j0;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp == 2 || warp == 3) {
+    // ================================ peer pushes ==================================
+    if (L.npush > 0) {
+      const long long w = (long long)blockIdx.x * 2 + (warp - 2);
+      const long long nw = (long long)gridDim.x * 2;
+      const char* src_base = L.peers[L.rank] + L.buf_off;
+      for (int sgi = 0; sgi < L.npush; ++sgi) {
+        const PushSeg& sg = L.push[sgi];
+        const long long units = (long long)(sg.bytes >> 4);
+        const uint4* src = reinterpret_cast<const uint4*>(src_base + sg.off);
+        constexpr int U = 4;
+        for (long long base = w * (32 * U); base < units; base += nw * (32 * U)) {
+          uint4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const long long i = base + u * 32 + lane;
+            if (i < units) v[u] = __ldcg(src + i);
+          }
+          for (int r = 0; r < L.world; ++r) {
+            if (r == L.rank) continue;
+            uint4* dst = reinterpret_cast<uint4*>(L.peers[r] + L.buf_off + sg.off);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const long long i = base + u * 32 + lane;
+              if (i < units) dst[i] = v[u];
+            }
+          }
+        }
+        if (sg.last_of_chan) {
+          // every lane: my stores are ordered before whatever I signal next
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0) {
+            const unsigned long long done = atomicAdd(L.tickets + sg.chan, 1ull) + 1ull;
+            if (done == L.ticket_target) {  // the last push warp of this launch for this channel
+              __threadfence_system();
+              if (sg.chan == L.status_chan) {
+                unsigned long long sv = L.status_val;
+                for (int b = 0; b < L.nbad; ++b)
+                  if (__ldcg(L.bad + b) == (unsigned long long)L.gen) sv &= ~1ull;
+                for (int r = 0; r < L.world; ++r)
+                  *reinterpret_cast<unsigned long long*>(L.peers[r] + L.buf_off + L.status_off +
+                                                         8ull * L.rank) = sv;
+              }
+              __threadfence_system();
+              for (int r = 0; r < L.world; ++r)
+                st_release_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[r]) +
+                                       sg.chan * kMaxRanks + L.rank,
+                                   L.seq);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
     // ================================ epilogue ====================================
     const int wg = (warp - 4) >> 2;  // column half of every tile this warpgroup reduces
     const int q = warp & 3;          // == warp % 4: TMEM lane quadrant
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;  // 0..255: one key factor per thread and tile
     const int ch0 = wg * (BN / 64);    // first of this warpgroup's BN/64 32-column chunks
-    const float s = kRank ? 1.f : *p.scale;
-    const bool neg = s < 0.f;
     uint32_t acc = 0;
+    int si = 0;
     for (long long t = t_begin; t < t_end;) {
-      const int qt = int(t / p.nkt), kt0 = int(t % p.nkt);
-      int kt1 = kt0 + int(t_end - t);
-      if (kt1 > p.nkt) kt1 = p.nkt;
+      si = find_sub(L, t, si);
+      const FwdSub& S = L.sub[si];
+      const long long local = t - S.tile_begin;
+      const int qt = int(local / S.nkt_sub), j0 = int(local % S.nkt_sub);
+      int j1 = j0 + int(t_end - t);
+      if (j1 > S.nkt_sub) j1 = S.nkt_sub;
+      const float* __restrict__ kinv = S.kinv;
+      const int nk = S.nk;
+      const float s = kRank ? 1.f : *S.scale;
+      const bool neg = s < 0.f;
       float m = -INFINITY, l = 0.f, tt = 0.f;
       const int grow = qt * BM + row;
+      auto tile_of = [&](int j) {
+        int kt = S.kt0 + j;
+        return kt >= S.nkt_all ? kt - S.nkt_all : kt;
+      };
       float knext;  // key factor of column `et` of the next tile (prefetched one tile ahead)
       {
-        const int gk = kt0 * BN + et;
-        knext = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+        const int gk = tile_of(j0) * BN + et;
+        knext = (kinv && gk < nk) ? kinv[gk] : 1.f;
       }
       if (kRank) {
         // count_j [ qinv_i * kinv_j * (q_i . k_j) > thr_i ]  ==  [ x_ij * kinv_j > thr_i / qinv_i ]
-        const float qi = (p.qinv && grow < p.nq) ? p.qinv[grow] : 1.f;
-        const float th = (grow < p.nq ? p.thr[grow] : INFINITY) / qi;
-        const long long tg = (p.tgt && grow < p.nq) ? p.tgt[grow] : -1;
+        const float qi = (S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f;
+        const float th = (grow < S.nq ? S.thr[grow] : INFINITY) / qi;
+        const long long tg = (S.tgt && grow < S.nq) ? S.tgt[grow] : -1;
         int cnt = 0;
-        for (int kt = kt0; kt < kt1; ++kt) {
+        for (int j = j0; j < j1; ++j) {
+          const int kt = tile_of(j);
           const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
           float* kv = sKinv + ab * BN;
           kv[et] = knext;  // fetched while the previous tile was being reduced
-          if (kt + 1 < kt1) {
-            const int gk = (kt + 1) * BN + et;
-            knext = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+          if (j + 1 < j1) {
+            const int gk = tile_of(j + 1) * BN + et;
+            knext = (kinv && gk < nk) ? kinv[gk] : 1.f;
           }
           named_bar_sync(1, 256);
           mbar_wait(&acc_full[ab], aphase);
           tc_fence_after();
           const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
-          const int valid = p.nk - kt * BN;
+          const int valid = nk - kt * BN;
 #pragma unroll 1
           for (int ch = ch0; ch < ch0 + BN / 64; ++ch) {
             uint32_t v[32];
@@ -244,20 +366,24 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         m = float(cnt);  // exact below 2^24 keys per segment
       } else {
       // logit = s * (q_i.k_j) * qinv_i * kinv_j ; c folds everything that depends on the row
-      const float c = s * LOG2E * ((p.qinv && grow < p.nq) ? p.qinv[grow] : 1.f);
-      for (int kt = kt0; kt < kt1; ++kt) {
+      const float c = s * LOG2E * ((S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f);
+      // the positive of this row is key row label_off + grow: picked out of the tile that holds it
+      const long long tg = (S.label_off >= 0 && S.pos && grow < S.nq) ? S.label_off + grow : -1;
+      for (int j = j0; j < j1; ++j) {
+        const int kt = tile_of(j);
         const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
         float* kv = sKinv + ab * BN;
         kv[et] = knext;  // fetched while the previous tile was being reduced
-        if (kt + 1 < kt1) {
-          const int gk = (kt + 1) * BN + et;
-          knext = (p.kinv && gk < p.nk) ? p.kinv[gk] : 1.f;
+        if (j + 1 < j1) {
+          const int gk = tile_of(j + 1) * BN + et;
+          knext = (kinv && gk < nk) ? kinv[gk] : 1.f;
         }
         named_bar_sync(1, 256);
         mbar_wait(&acc_full[ab], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
-        const int valid = p.nk - kt * BN;  // columns of this tile that exist (>= 1)
+        const int valid = nk - kt * BN;  // columns of this tile that exist (>= 1)
+        const long long tcol = tg - (long long)kt * BN;  // the positive's column in this tile, if any
         // One 32-column chunk: multiply by the key factors, update the running maximum, add the
         // exponentials.  Packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2) with two interleaved
         // partial sums halves the FP32 instruction count next to the MUFU work.
@@ -276,6 +402,14 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                                       __uint_as_float(v[4 * e4 + 3])),
                                           make_float2(f.z, f.w));
             }
+          }
+          const long long tl = tcol - ch * 32;
+          if (tl >= 0 && tl < 32 && tl < cv) {  // (rare) this chunk holds the row's positive
+            float px = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e == int(tl)) px = (e & 1) ? x2[e >> 1].y : x2[e >> 1].x;
+            S.pos[grow] = px * c * LN2;
           }
           if (cv >= 32) {
             float ext = x2[0].x;
@@ -345,15 +479,16 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ++acc;
       }
       }
-      // partial statistics of this (q-tile, key range) segment
-      const long long first_tile = (long long)qt * p.nkt;
-      const int c_first = int(first_tile / p.tiles_per_cta);
+      // partial statistics of this (sub-problem, q-tile, key range) segment
+      const long long first_tile = S.tile_begin + (long long)qt * S.nkt_sub;
+      const int c_first = int(first_tile / L.tiles_per_cta);
       const int slot = 2 * (int(blockIdx.x) - c_first) + wg;  // one partial per column half
-      const long long o = (long long)slot * p.part_stride + (long long)qt * BM + row;
-      p.part_m[o] = m;
-      p.part_l[o] = l;
-      p.part_t[o] = tt;
-      t += kt1 - kt0;
+      const long long stride = (long long)S.nqt * BM;
+      const long long o = (long long)slot * stride + (long long)qt * BM + row;
+      S.part[o] = m;
+      S.part[(long long)S.max_slots * stride + o] = l;
+      S.part[2ll * S.max_slots * stride + o] = tt;
+      t += j1 - j0;
     }
   }
   tc_fence_before();
@@ -361,102 +496,165 @@ sim_lse_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-// Merge the per-CTA partial statistics of each row.
-__global__ void lse_combine_kernel(FwdParams p, float* __restrict__ lse, float* __restrict__ esum) {
+// Merge the per-CTA partial statistics of each row (single sub-problem launches of the ABI).
+__global__ void lse_combine_kernel(FwdSub S, int tiles_per_cta, float* __restrict__ lse,
+                                   float* __restrict__ esum) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= p.nq) return;
-  const int qt = row / BM;
-  const long long first_tile = (long long)qt * p.nkt;
-  const int c_first = int(first_tile / p.tiles_per_cta);
-  const int c_last = int((first_tile + p.nkt - 1) / p.tiles_per_cta);
-  const int nslots = 2 * (c_last - c_first + 1);  // two column halves per CTA segment
-  float M = -INFINITY;
-  for (int s = 0; s < nslots; ++s)
-    M = fmaxf(M, p.part_m[(long long)s * p.part_stride + row]);
-  float L = 0.f, T = 0.f;
-  for (int s = 0; s < nslots; ++s) {
-    const long long o = (long long)s * p.part_stride + row;
-    const float w = exp2f(p.part_m[o] - M);
-    L += p.part_l[o] * w;
-    T += p.part_t[o] * w;
-  }
-  const float sc = (*p.scale) * (p.qinv ? p.qinv[row] : 1.f);
-  lse[row] = (M + log2f(L)) * LN2;
-  if (esum) esum[row] = sc * T / L;
+  if (row >= S.nq) return;
+  float M, Lsum, T;
+  fwd_combine_row(S, tiles_per_cta, row, &M, &Lsum, &T);
+  const float sc = (*S.scale) * (S.qinv ? S.qinv[row] : 1.f);
+  lse[row] = (M + log2f(Lsum)) * LN2;
+  if (esum) esum[row] = sc * T / Lsum;
 }
 
 // Rank mode: total count of each row over the key segments of different CTAs.
-__global__ void rank_combine_kernel(FwdParams p, long long* __restrict__ rank) {
+__global__ void rank_combine_kernel(FwdSub S, int tiles_per_cta, long long* __restrict__ rank) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= p.nq) return;
+  if (row >= S.nq) return;
   const int qt = row / BM;
-  const long long first_tile = (long long)qt * p.nkt;
-  const int c_first = int(first_tile / p.tiles_per_cta);
-  const int c_last = int((first_tile + p.nkt - 1) / p.tiles_per_cta);
+  const long long first_tile = S.tile_begin + (long long)qt * S.nkt_sub;
+  const int c_first = int(first_tile / tiles_per_cta);
+  const int c_last = int((first_tile + S.nkt_sub - 1) / tiles_per_cta);
+  const long long stride = (long long)S.nqt * BM;
   long long total = 0;
   for (int s = 0; s < 2 * (c_last - c_first + 1); ++s)
-    total += (long long)p.part_m[(long long)s * p.part_stride + row];
+    total += (long long)S.part[(long long)s * stride + row];
   rank[row] = total;
-}
-
-int fwd_plan(int num_sms, long long nq, long long nk, long long d, FwdParams* p, bool* qres,
-             size_t* smem_bytes) {
-  p->nq = int(nq);
-  p->nk = int(nk);
-  p->kchunks = int((d + BK - 1) / BK);
-  p->nqt = int((nq + BM - 1) / BM);
-  p->nkt = int((nk + BN - 1) / BN);
-  p->total_tiles = (long long)p->nqt * p->nkt;
-  long long ctas = p->total_tiles < num_sms ? p->total_tiles : num_sms;
-  p->tiles_per_cta = int((p->total_tiles + ctas - 1) / ctas);
-  p->max_slots = 2 * ((p->nkt + p->tiles_per_cta - 1) / p->tiles_per_cta + 1);  // x2: column halves
-  p->part_stride = (long long)p->nqt * BM;
-  const size_t budget = 227 * 1024 - 256 /*barriers*/ - 2 * BN * sizeof(float) /*kinv*/;
-  *qres = size_t(p->kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= budget;
-  const size_t stage_bytes = *qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
-  const size_t fixed = *qres ? size_t(p->kchunks) * QCHUNK_BYTES : 0;
-  int ns = int((budget - fixed) / stage_bytes);
-  if (ns > 8) ns = 8;
-  p->nstages = ns;
-  *smem_bytes = fixed + ns * stage_bytes + 2 * BN * sizeof(float) + 256;
-  return 0;
 }
 
 }  // namespace
 
-size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d) {
-  FwdParams p;
-  bool qres;
-  size_t smem;
-  fwd_plan(num_sms, nq, nk, d, &p, &qres, &smem);
-  return size_t(3) * p.max_slots * p.part_stride * sizeof(float);
+// ---- planning (host) ---------------------------------------------------------------------------
+
+void fwd_begin(FwdLaunch* L, long long d) {
+  *L = FwdLaunch();
+  L->nsub = 0;
+  L->total_tiles = 0;
+  L->kchunks = int((d + BK - 1) / BK);
+  L->world = 1;
+  L->rank = 0;
+  L->rows_per_rank = 1;
+  L->npush = 0;
+  L->status_chan = -1;
 }
 
-namespace {
+int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub) {
+  if (L->nsub >= kMaxFwdSubs) return -1;
+  FwdSub& S = L->sub[L->nsub];
+  S = FwdSub();
+  S.nq = int(nq);
+  S.nk = int(nk);
+  S.nqt = int((nq + BM - 1) / BM);
+  S.nkt_all = int((nk + BN - 1) / BN);
+  S.kt0 = kt0;
+  S.nkt_sub = nkt_sub < 0 ? S.nkt_all : nkt_sub;
+  S.tile_begin = L->total_tiles;
+  S.label_off = -1;
+  S.chan = kChanRows;
+  L->total_tiles += (long long)S.nqt * S.nkt_sub;
+  return L->nsub++;
+}
+
+static size_t fwd_smem_budget() { return 227 * 1024 - 256 /*barriers*/ - 2 * BN * sizeof(float); }
+
+// Fixes the CTA split; returns the bytes of partial statistics the launch needs and the offset of
+// every sub-problem's partials inside that block (part_off[i], in floats).
+size_t fwd_finish(FwdLaunch* L, int num_sms, size_t* part_off) {
+  long long ctas = L->total_tiles < num_sms ? L->total_tiles : num_sms;
+  if (ctas < 1) ctas = 1;
+  L->tiles_per_cta = int((L->total_tiles + ctas - 1) / ctas);
+  if (L->tiles_per_cta < 1) L->tiles_per_cta = 1;
+  const size_t budget = fwd_smem_budget();
+  const bool qres = size_t(L->kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= budget;
+  const size_t stage_bytes = qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
+  const size_t fixed = qres ? size_t(L->kchunks) * QCHUNK_BYTES : 0;
+  int ns = int((budget - fixed) / stage_bytes);
+  if (ns > 8) ns = 8;
+  L->nstages = ns;
+  size_t floats = 0;
+  for (int i = 0; i < L->nsub; ++i) {
+    FwdSub& S = L->sub[i];
+    // x2: column halves; +1: a range may start inside the sub-problem's first CTA share
+    S.max_slots = 2 * ((S.nkt_sub + L->tiles_per_cta - 1) / L->tiles_per_cta + 1);
+    if (part_off) part_off[i] = floats;
+    floats += size_t(3) * S.max_slots * size_t(S.nqt) * BM;
+  }
+  return floats * sizeof(float);
+}
+
+static bool fwd_qres(const FwdLaunch& L) {
+  return size_t(L.kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= fwd_smem_budget();
+}
 
 template <bool kRank>
-cudaError_t launch_fwd(int num_sms, const void* q, long long nq, const void* k, long long nk,
-                       long long d, FwdParams p, bool qres, size_t smem, cudaStream_t stream,
-                       const char** err) {
-  CUtensorMap tmQ, tmK;
-  if (make_tmap_bf16_sw128(&tmQ, q, nq, d, d, BM) || make_tmap_bf16_sw128(&tmK, k, nk, d, d, BN)) {
-    *err = "sim_fwd: cuTensorMapEncodeTiled failed";
-    return cudaErrorInvalidValue;
-  }
-  const int ctas = int((p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
+static cudaError_t launch_fwd(const TensorMaps& maps, const FwdLaunch& L, cudaStream_t stream) {
+  const bool qres = fwd_qres(L);
+  const size_t stage_bytes = qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
+  const size_t smem = (qres ? size_t(L.kchunks) * QCHUNK_BYTES : 0) + L.nstages * stage_bytes +
+                      2 * BN * sizeof(float) + 256;
+  const int ctas = int((L.total_tiles + L.tiles_per_cta - 1) / L.tiles_per_cta);
   cudaError_t e;
   if (qres) {
     e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true, kRank>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<true, kRank><<<ctas, 384, smem, stream>>>(tmQ, tmK, p);
+    sim_lse_fwd_kernel<true, kRank><<<ctas, 384, smem, stream>>>(maps, L);
   } else {
     e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false, kRank>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<false, kRank><<<ctas, 384, smem, stream>>>(tmQ, tmK, p);
+    sim_lse_fwd_kernel<false, kRank><<<ctas, 384, smem, stream>>>(maps, L);
   }
+  count_launches(1);
   return cudaGetLastError();
+}
+
+int fwd_grid(const FwdLaunch& L) {
+  return int((L.total_tiles + L.tiles_per_cta - 1) / L.tiles_per_cta);
+}
+
+cudaError_t launch_fwd_fused(const TensorMaps& maps, const FwdLaunch& L, cudaStream_t stream) {
+  if (L.total_tiles == 0) return cudaSuccess;
+  return launch_fwd<false>(maps, L, stream);
+}
+
+int fwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d) {
+  if (slot < 0 || 2 * slot + 1 >= kMaxFwdMaps) return -1;
+  if (make_tmap_bf16_sw128(&maps->tm[2 * slot], rows, n, d, d, BM)) return -1;
+  if (make_tmap_bf16_sw128(&maps->tm[2 * slot + 1], rows, n, d, d, BN)) return -1;
+  return 0;
+}
+
+size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d) {
+  FwdLaunch L;
+  fwd_begin(&L, d);
+  fwd_add_sub(&L, nq, nk, 0, -1);
+  return fwd_finish(&L, num_sms, nullptr);
+}
+
+namespace {
+
+cudaError_t single_problem(int num_sms, const void* q, long long nq, const void* k, long long nk,
+                           long long d, void* workspace, size_t workspace_bytes, FwdLaunch* L,
+                           TensorMaps* maps, const char** err, const char* who) {
+  fwd_begin(L, d);
+  fwd_add_sub(L, nq, nk, 0, -1);
+  size_t off = 0;
+  const size_t need = fwd_finish(L, num_sms, &off);
+  if (workspace_bytes < need) {
+    *err = who;
+    return cudaErrorInvalidValue;
+  }
+  if (make_tmap_bf16_sw128(&maps->tm[0], q, nq, d, d, BM) ||
+      make_tmap_bf16_sw128(&maps->tm[1], k, nk, d, d, BN)) {
+    *err = "sim_fwd: cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  L->sub[0].map_q = 0;
+  L->sub[0].map_k = 1;
+  L->sub[0].part = static_cast<float*>(workspace);
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -465,27 +663,19 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
                                long long nk, long long d, const float* scale, const float* qinv,
                                const float* kinv, float* lse, float* esum, void* workspace,
                                size_t workspace_bytes, cudaStream_t stream, const char** err) {
-  FwdParams p;
-  bool qres;
-  size_t smem;
-  fwd_plan(num_sms, nq, nk, d, &p, &qres, &smem);
-  const size_t need = size_t(3) * p.max_slots * p.part_stride * sizeof(float);
-  if (workspace_bytes < need) {
-    *err = "sim_lse_fwd: workspace too small";
-    return cudaErrorInvalidValue;
-  }
-  p.scale = scale;
-  p.qinv = qinv;
-  p.kinv = kinv;
-  p.thr = nullptr;
-  p.tgt = nullptr;
-  p.part_m = static_cast<float*>(workspace);
-  p.part_l = p.part_m + size_t(p.max_slots) * p.part_stride;
-  p.part_t = p.part_l + size_t(p.max_slots) * p.part_stride;
-  cudaError_t e = launch_fwd<false>(num_sms, q, nq, k, nk, d, p, qres, smem, stream, err);
+  FwdLaunch L;
+  TensorMaps maps;
+  cudaError_t e = single_problem(num_sms, q, nq, k, nk, d, workspace, workspace_bytes, &L, &maps,
+                                 err, "sim_lse_fwd: workspace too small");
   if (e != cudaSuccess) return e;
-  lse_combine_kernel<<<(p.nq + 255) / 256, 256, 0, stream>>>(p, lse, esum);
-  count_launches(2);
+  L.sub[0].scale = scale;
+  L.sub[0].qinv = qinv;
+  L.sub[0].kinv = kinv;
+  e = launch_fwd<false>(maps, L, stream);
+  if (e != cudaSuccess) return e;
+  lse_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], L.tiles_per_cta, lse,
+                                                                    esum);
+  count_launches(1);
   return cudaGetLastError();
 }
 
@@ -494,27 +684,20 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
                                 const float* thr, const long long* tgt, long long* rank,
                                 void* workspace, size_t workspace_bytes, cudaStream_t stream,
                                 const char** err) {
-  FwdParams p;
-  bool qres;
-  size_t smem;
-  fwd_plan(num_sms, nq, nk, d, &p, &qres, &smem);
-  const size_t need = size_t(3) * p.max_slots * p.part_stride * sizeof(float);
-  if (workspace_bytes < need) {
-    *err = "sim_rank_fwd: workspace too small";
-    return cudaErrorInvalidValue;
-  }
-  p.scale = nullptr;
-  p.qinv = qinv;
-  p.kinv = kinv;
-  p.thr = thr;
-  p.tgt = tgt;
-  p.part_m = static_cast<float*>(workspace);
-  p.part_l = p.part_m + size_t(p.max_slots) * p.part_stride;
-  p.part_t = p.part_l + size_t(p.max_slots) * p.part_stride;
-  cudaError_t e = launch_fwd<true>(num_sms, q, nq, k, nk, d, p, qres, smem, stream, err);
+  FwdLaunch L;
+  TensorMaps maps;
+  cudaError_t e = single_problem(num_sms, q, nq, k, nk, d, workspace, workspace_bytes, &L, &maps,
+                                 err, "sim_rank_fwd: workspace too small");
   if (e != cudaSuccess) return e;
-  rank_combine_kernel<<<(p.nq + 255) / 256, 256, 0, stream>>>(p, rank);
-  count_launches(2);
+  L.sub[0].qinv = qinv;
+  L.sub[0].kinv = kinv;
+  L.sub[0].thr = thr;
+  L.sub[0].tgt = tgt;
+  e = launch_fwd<true>(maps, L, stream);
+  if (e != cudaSuccess) return e;
+  rank_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], L.tiles_per_cta,
+                                                                     rank);
+  count_launches(1);
   return cudaGetLastError();
 }
 

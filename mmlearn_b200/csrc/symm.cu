@@ -26,8 +26,7 @@ namespace mmcl {
 
 namespace {
 
-constexpr size_t kFlagBytes = 1024;  // kFenceChannels x kMaxRanks 64-bit flag words
-constexpr int kMaxRanks = 32;
+// flag words: fused.h (kFlagBytes, kMaxRanks; channels 0..kFenceChannels-1 are fence channels)
 
 template <typename V>  // uint4 (16-byte units) or uint32_t (4-byte units)
 __global__ void symm_put_kernel(char* const* __restrict__ peers, int world, size_t dst_off,
@@ -252,6 +251,7 @@ int symm_reserve(SymmArena* a, void* comm_v, int rank, int world, size_t bytes,
   a->local = base;
   a->bytes = bytes;
   for (auto& q : a->seq) q = 0;
+  a->step_seq = 0;
   return 0;
 }
 

@@ -152,6 +152,7 @@ class _ArenaState:
 
     def __init__(self):
         self.step = 0
+        self.capacity = 0          # bytes per buffer of the current allocation
         self.owner = [None, None]  # weakref to the _Run whose saved tensors live in the buffer
         self.disabled = os.environ.get("MMCL_NO_SYMM", "0") == "1"
         self.views: dict = {}
@@ -178,10 +179,22 @@ class _Transport:
         if a.disabled:
             return
         parity = a.step & 1
-        prev = a.owner[parity]() if a.owner[parity] is not None else None
-        if prev is not None and prev is not run and prev.states:
-            return  # a run that was not back-propagated yet still reads this buffer: use NCCL
-        if self.lib.mmcl_symm_reserve(self.h, max(need_bytes, 1 << 20), self.st) != 0:
+
+        def busy(ref):
+            """A buffer is claimed by a run that wants gradients and has not been back-propagated
+            (or released) yet.  All of that is protocol state every rank shares as long as the
+            ranks call forward / backward symmetrically, which DDP training does."""
+            prev = ref() if ref is not None else None
+            return (prev is not None and prev is not run and bool(prev.states)
+                    and prev.backward_calls == 0)
+
+        if busy(a.owner[parity]):
+            return  # that run still reads this buffer: use NCCL for this step
+        need = max(need_bytes, 1 << 20)
+        if a.capacity and need > a.capacity and busy(a.owner[parity ^ 1]):
+            # growing re-allocates BOTH buffers; the other one still holds a run's saved state
+            return
+        if self.lib.mmcl_symm_reserve(self.h, need, self.st) != 0:
             a.disabled = True  # agreed on by all ranks inside the call
             return
         out, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
@@ -192,12 +205,13 @@ class _Transport:
             a.views = {k_: v for k_, v in a.views.items() if k_[0] != parity}
             a.views[vkey] = torch.as_tensor(_Raw(out.value, nbytes.value), device=self.dev)
         self.base = a.views[vkey]
-        self.capacity = nbytes.value
+        self.capacity = a.capacity = nbytes.value
         self.parity = parity
         self.cursor = 0
         self.arena = True
         a.step += 1
         a.owner[parity] = weakref.ref(run)
+        run.arena_claim = (a, parity)
 
     # ---- arena primitives ----
     def alloc(self, nbytes: int) -> int:
@@ -281,6 +295,8 @@ class _Run:
         self.example_ids = example_ids
         self.pairs = pairs
         self.states: list[_PairState] = []
+        self.backward_calls = 0
+        self.arena_claim = None  # (_ArenaState, parity) when the saved state lives in the arena
 
     # ------------------------------------------------------------------------------------
     def forward(self, logit_scale: torch.Tensor, embs):
@@ -361,10 +377,15 @@ class _Run:
         es = [self.embs.get(Modalities.get_modality(n).embedding) for n in names]
         if any(e is None or e.dtype not in _DTYPES for e in es):
             return None  # cannot happen with this table; stay on the general path
-        sp = SteadyPlan(self.h, world, rank, rows, es[0].shape[-1], names,
-                        [_DTYPES[e.dtype] for e in es], [bool(e.requires_grad) for e in es],
-                        self.pairs, pair_mods, int(self.scale.numel()), self.m.l2_normalize,
-                        self.m.local_loss, self.m.gather_with_grad, bool(self.need_grad))
+        try:
+            sp = SteadyPlan(self.h, world, rank, rows, es[0].shape[-1], names,
+                            [_DTYPES[e.dtype] for e in es], [bool(e.requires_grad) for e in es],
+                            self.pairs, pair_mods, int(self.scale.numel()), self.m.l2_normalize,
+                            self.m.local_loss, self.m.gather_with_grad, bool(self.need_grad))
+        except MmclError:
+            # outside the fused step's limits (more than 6 modalities / 4 pairs, rows % 4 with
+            # several ranks): shapes are rank-identical, so every rank stays on the general path
+            return None
         sp.shared_key = self._shared_key()
         return sp
 
@@ -764,7 +785,28 @@ class _Run:
                           "mmcl_sim_grad_bwd")
                 stt.dacc[side] = dacc
 
+    def _check_saved_state(self) -> None:
+        """Second and later backward passes through the same loss (retain_graph=True): the saved
+        state is kept until the autograd node dies, but state that lives in the symmetric arena
+        may have been overwritten by a later forward, which must not pass silently."""
+        self.backward_calls += 1
+        if self.backward_calls == 1:
+            return
+        if not self.states:
+            raise RuntimeError(
+                "Trying to backward through the fused contrastive loss a second time, but its "
+                "saved state has already been released.")
+        if self.arena_claim is not None:
+            a, parity = self.arena_claim
+            owner = a.owner[parity]() if a.owner[parity] is not None else None
+            if owner is not self:
+                raise RuntimeError(
+                    "Trying to backward through the fused contrastive loss a second time after a "
+                    "later forward has reused its gather buffer; run the second backward before "
+                    "the next-but-one forward of this process.")
+
     def _backward_steady(self, gout: torch.Tensor):
+        self._check_saved_state()
         sp, parity, es, ws = self.fast
         dev = self.dev
         st = _stream(dev)
@@ -783,12 +825,12 @@ class _Run:
                 out.append(by_key[key])
             else:
                 out.append(torch.zeros_like(src))
-        self.release()
         return out
 
     def backward(self, gout: torch.Tensor):
         if self.fast is not None:
             return self._backward_steady(gout)
+        self._check_saved_state()
         lib = _lib.load()
         dev, h = self.dev, self.h
         st = _stream(dev)
@@ -851,7 +893,6 @@ class _Run:
                 out.append(grads32[key].to(src.dtype))
             else:
                 out.append(torch.zeros_like(src))
-        self.states = []
         return out
 
 

@@ -233,3 +233,26 @@ def test_single_cta_backward_kernel_still_matches():
                         "-k", "sim_grad_bwd", "-m", "gpu"], cwd=root, env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_backward_twice_with_retain_graph():
+    """A second backward through the same loss (retain_graph=True) gives the same gradients again
+    on the general path and on the native-step path; it never returns zeros silently."""
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    n, d = 384, 128
+    emb, ids = synthetic_inputs(n, d)
+    fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    pairs = [LossPairSpec(("rgb", "text"))]
+    idt = {k: torch.from_numpy(v).to(DEV) for k, v in ids[0].items()}
+    for step in range(3):  # step 0: general path, later steps: native step executor
+        leaves = {k: v.to(DEV).clone().requires_grad_(True) for k, v in emb[0].items()}
+        s = torch.tensor(1 / 0.07, device=DEV, requires_grad=True)
+        loss = fn(leaves, idt, s, pairs)
+        g1 = torch.autograd.grad(loss, list(leaves.values()) + [s], retain_graph=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        for (k, v), g in zip(list(leaves.items()) + [("scale", s)], g1):
+            assert float(g.float().norm()) > 0
+            torch.testing.assert_close(v.grad, g, rtol=0, atol=0)
+    assert fn.steady_steps == 2

@@ -47,8 +47,9 @@ def test_steady_steps_match_general_path_and_oracle(n, d, dtype, l2):
         loss, leaves, s = _step(fn, emb[0], ids[0], scale, pairs, dtype)
         assert fn.steady_steps == k
         _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
-        # same kernels in the same order as the general path: equal up to atomic ordering
-        assert float(loss) == pytest.approx(float(first[0]), rel=1e-6)
+        # same arithmetic as the general path, except that the fused step takes the positive logit
+        # out of the tensor-core tile (another fp32 summation order than the dot-product kernel)
+        assert float(loss) == pytest.approx(float(first[0]), rel=2e-5)
         for key in leaves:  # (fp32 atomics may reorder; a bf16 output may flip its last bit)
             g0, g1 = first[1][key].grad.float(), leaves[key].grad.float()
             assert float((g1 - g0).norm()) <= 2e-3 * float(g0.norm())
