@@ -291,6 +291,8 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
     const int ch0 = wg * (BN / 64);    // first of this warpgroup's BN/64 32-column chunks
     uint32_t acc = 0;
     int si = 0;
+    int kseen_chan = -1;
+    uint32_t kseen = 0;
     for (long long t = t_begin; t < t_end;) {
       si = find_sub(L, t, si);
       const FwdSub& S = L.sub[si];
@@ -298,7 +300,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       const int qt = int(local / S.nkt_sub), j0 = int(local % S.nkt_sub);
       int j1 = j0 + int(t_end - t);
       if (j1 > S.nkt_sub) j1 = S.nkt_sub;
-      const float* __restrict__ kinv = S.kinv;
+      const float* kinv = S.kinv;
       const int nk = S.nk;
       const float s = kRank ? 1.f : *S.scale;
       const bool neg = s < 0.f;
@@ -308,11 +310,27 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         int kt = S.kt0 + j;
         return kt >= S.nkt_all ? kt - S.nkt_all : kt;
       };
-      float knext;  // key factor of column `et` of the next tile (prefetched one tile ahead)
-      {
-        const int gk = tile_of(j0) * BN + et;
-        knext = (kinv && gk < nk) ? kinv[gk] : 1.f;
+      // Key factor of column `et` of tile kt.  With several ranks the factors of another rank's
+      // rows arrive by peer stores like the rows themselves: this thread acquires the source
+      // rank's ready flag before its first read (the TMA producer waits on the same flag, so a
+      // stall here never delays a tile that could otherwise run).
+      if (S.chan != kseen_chan) {
+        kseen_chan = S.chan;
+        kseen = 0;
       }
+      auto key_factor = [&](int kt) -> float {
+        const int gk = kt * BN + et;
+        if (!(kinv && gk < nk)) return 1.f;
+        if (L.world > 1) {
+          const int r = gk / int(L.rows_per_rank);
+          if (r != L.rank && r < L.world && !((kseen >> r) & 1u)) {
+            wait_flag(L.flags + S.chan * kMaxRanks + r, L.seq, L.err);
+            kseen |= 1u << r;
+          }
+        }
+        return __ldcg(kinv + gk);
+      };
+      float knext = key_factor(tile_of(j0));  // prefetched one tile ahead
       if (kRank) {
         // count_j [ qinv_i * kinv_j * (q_i . k_j) > thr_i ]  ==  [ x_ij * kinv_j > thr_i / qinv_i ]
         const float qi = (S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f;
@@ -324,10 +342,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
           const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
           float* kv = sKinv + ab * BN;
           kv[et] = knext;  // fetched while the previous tile was being reduced
-          if (j + 1 < j1) {
-            const int gk = tile_of(j + 1) * BN + et;
-            knext = (kinv && gk < nk) ? kinv[gk] : 1.f;
-          }
+          if (j + 1 < j1) knext = key_factor(tile_of(j + 1));
           named_bar_sync(1, 256);
           mbar_wait(&acc_full[ab], aphase);
           tc_fence_after();
@@ -374,10 +389,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
         float* kv = sKinv + ab * BN;
         kv[et] = knext;  // fetched while the previous tile was being reduced
-        if (j + 1 < j1) {
-          const int gk = tile_of(j + 1) * BN + et;
-          knext = (kinv && gk < nk) ? kinv[gk] : 1.f;
-        }
+        if (j + 1 < j1) knext = key_factor(tile_of(j + 1));
         named_bar_sync(1, 256);
         mbar_wait(&acc_full[ab], aphase);
         tc_fence_after();

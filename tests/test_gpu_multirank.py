@@ -122,15 +122,15 @@ def test_speculation_sequence_two_ranks():
         mp.spawn(_worker_sequence, args=(2, names, os.path.join(td, "init"), ret), nprocs=2,
                  join=True)
     for r in range(2):
-        for name, got in zip(names, ret[r]):
+        for step, (name, got) in enumerate(zip(names, ret[r])):
             ref = load_case(name)["out"][r]
-            assert got["loss"] == pytest.approx(float(ref["loss"]), rel=1e-3, abs=1e-6), name
+            assert got["loss"] == pytest.approx(float(ref["loss"]), rel=1e-3, abs=1e-6), (name, step)
             for k in [k for k in got if k.startswith("grad_")]:
                 g, e = torch.from_numpy(got[k]), torch.from_numpy(ref[k])
                 if float(e.norm()) == 0:
                     assert float(g.norm()) == 0
                     continue
-                assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2), (name, k)
+                assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2), (name, step, k, r)
 
 
 def test_nccl_transport_two_ranks():
