@@ -336,6 +336,7 @@ def main():
     issue_copy(0)
     read_ev = [None, None]
     e2e_losses = []
+    host_t = []
     for i in range(total):
         if i + 1 < total:
             issue_copy(i + 1)
@@ -353,6 +354,7 @@ def main():
         if i >= 1:  # the host consumes step i-1's loss now (logging lags by one step)
             read_ev[(i - 1) % 2].synchronize()
             e2e_losses.append(float(out_host[(i - 1) % 2][0]))
+        host_t.append(time.perf_counter())
     read_ev[(total - 1) % 2].synchronize()
     e2e_losses.append(float(out_host[(total - 1) % 2][0]))
     barrier()
@@ -360,6 +362,7 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = N / (float(t2) / e2e_steps * 1e-3)
+    host_dt = sorted((b_ - a_) * 1e3 for a_, b_ in zip(host_t[2:-1], host_t[3:]))
     h2d = sum(h_emb[m].numel() * 2 for m in mods) + h_ids.numel() * 8 + 4 * max(P, 1)
     d2h = 4 * (1 + max(P, 1))
     e2e_ok = all(math.isfinite(v) and abs(v - loss_value) <= 1e-3 * abs(loss_value)
@@ -531,6 +534,10 @@ def main():
                        "parallelism": f"dp{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
+                    "host_ms_per_step": {"median": host_dt[len(host_dt) // 2] if host_dt else None,
+                                         "max": host_dt[-1] if host_dt else None,
+                                         "note": "rank 0's host loop period; a single long step "
+                                                 "(allocator, page faults) shows up as max >> median"},
                     "how": "one event pair over all K steps incl. H2D copies, L2 flushes, kernels "
                            "and the D2H copy of loss + d(log scale) every step; the next step's "
                            "H2D is prefetched on a copy stream (double-buffered inputs); the host "

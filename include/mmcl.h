@@ -127,6 +127,12 @@ int mmcl_pack_rows_symm(mmcl_handle* h, int parity, const void* src, int src_dty
                         int normalize, size_t dst_off_rows, int64_t dst_off_inv,
                         mmcl_stream stream);
 int mmcl_symm_fence(mmcl_handle* h, mmcl_stream stream);
+/* Diagnostic (tools/push_bench.py): push `bytes` at offset `off` of this rank's buffer to the same
+ * offset of every peer's buffer.  mode 0: store kernel with the given grid; mode 1: one
+ * cudaMemcpyAsync per peer on `stream`; mode 2: one per peer on internal side streams (joined
+ * back into `stream`).  Not used by the loss. */
+int mmcl_debug_push(mmcl_handle* h, int parity, size_t off, size_t bytes, int mode, int blocks,
+                    int threads, mmcl_stream stream);
 
 /* Bracket several collective calls so that NCCL launches them as one fused operation
  * (ncclGroupStart / ncclGroupEnd); no-ops for world == 1. */

@@ -207,6 +207,20 @@ int mmcl_pack_rows_symm(mmcl_handle* h, int parity, const void* src, int src_dty
   return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_pack_rows_symm");
 }
 
+int mmcl_debug_push(mmcl_handle* h, int parity, size_t off, size_t bytes, int mode, int blocks,
+                    int threads, mmcl_stream stream) {
+  REQUIRE(h && h->world > 1 && h->arena.local, "mmcl_debug_push: no arena");
+  REQUIRE(bytes % 16 == 0 && off % 16 == 0 && off + bytes <= h->arena.bytes,
+          "mmcl_debug_push: bad range");
+  REQUIRE(mode >= 0 && mode <= 2 && (mode != 0 || (blocks > 0 && threads > 0 && threads <= 1024)),
+          "mmcl_debug_push: bad mode / grid");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaError_t e = debug_push(&h->arena, h->world, h->rank, parity, off, bytes, mode, blocks, threads,
+                             static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? MMCL_OK : cuda_fail(e, "mmcl_debug_push");
+}
+
 int mmcl_symm_fence(mmcl_handle* h, mmcl_stream stream) {
   REQUIRE(h && h->arena.local, "mmcl_symm_fence: no arena reserved");
   std::lock_guard<std::mutex> lk(h->mu);

@@ -32,6 +32,8 @@ struct FwdSub {  // one direction of one pair, restricted to a rotated range of 
   int nq, nk, nqt;
   int nkt_all, kt0, nkt_sub;  // key tile j in [0, nkt_sub) is global tile (kt0 + j) % nkt_all
   long long tile_begin;       // position in the launch's linear tile space
+  long long phase_begin;      // first tile of the phase this sub-problem belongs to
+  int tpc;                    // tiles per CTA of that phase
   int map_q, map_k;
   int max_slots;
   int chan;                   // flag channel that guards remote rows of K (world > 1)
@@ -53,9 +55,19 @@ struct PushSeg {
   int last_of_chan;          // 1: release after this segment
 };
 
+// The tile space is a sequence of PHASES; every CTA takes an equal contiguous share of each phase
+// and walks the phases in order ("local keys of every direction", then "remote keys of direction
+// a", ...), so all SMs work on what is available first.
+constexpr int kMaxFwdPhases = 4;
+struct FwdPhase {
+  long long tile_begin, total;
+  int tiles_per_cta;
+};
+
 struct FwdLaunch {
-  int nsub, kchunks, nstages, tiles_per_cta;
+  int nsub, kchunks, nstages, nphase, ctas;
   long long total_tiles;
+  FwdPhase phase[kMaxFwdPhases];
   // several ranks
   int world, rank;
   long long rows_per_rank;              // source rank of key row g = g / rows_per_rank

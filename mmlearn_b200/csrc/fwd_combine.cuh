@@ -1,6 +1,6 @@
 // Merging the forward kernel's partial row statistics (device code shared by sim_fwd.cu and the
 // step's post-forward kernel).  A (sub-problem, q-tile) item is covered by the CTAs
-// c_first..c_last of the launch's linear tile split; CTA c wrote its partials of the item into
+// c_first..c_last of its phase's linear tile split; CTA c wrote its partials of the item into
 // slots 2*(c - c_first) and 2*(c - c_first) + 1 (one per column half of the 128x256 tiles).
 #pragma once
 #include "fused.h"
@@ -9,12 +9,12 @@ namespace mmcl {
 
 // folds the partials of `row` of sub-problem S into the running (M, L, T): max (log2 units), sum
 // of 2^(x - M), sum of 2^(x - M) * cos
-__device__ __forceinline__ void fwd_merge_row(const FwdSub& S, int tiles_per_cta, int row,
-                                              float* M, float* L, float* T) {
+__device__ __forceinline__ void fwd_merge_row(const FwdSub& S, int row, float* M, float* L,
+                                              float* T) {
   const int qt = row / 128;
-  const long long first_tile = S.tile_begin + (long long)qt * S.nkt_sub;
-  const int c_first = int(first_tile / tiles_per_cta);
-  const int c_last = int((first_tile + S.nkt_sub - 1) / tiles_per_cta);
+  const long long first_tile = S.tile_begin - S.phase_begin + (long long)qt * S.nkt_sub;
+  const int c_first = int(first_tile / S.tpc);
+  const int c_last = int((first_tile + S.nkt_sub - 1) / S.tpc);
   const int nslots = 2 * (c_last - c_first + 1);
   const long long stride = (long long)S.nqt * 128;
   const float* pm = S.part;
@@ -36,12 +36,12 @@ __device__ __forceinline__ void fwd_merge_row(const FwdSub& S, int tiles_per_cta
   *T = t;
 }
 
-__device__ __forceinline__ void fwd_combine_row(const FwdSub& S, int tiles_per_cta, int row,
-                                                float* M, float* L, float* T) {
+__device__ __forceinline__ void fwd_combine_row(const FwdSub& S, int row, float* M, float* L,
+                                                float* T) {
   *M = -INFINITY;
   *L = 0.f;
   *T = 0.f;
-  fwd_merge_row(S, tiles_per_cta, row, M, L, T);
+  fwd_merge_row(S, row, M, L, T);
 }
 
 }  // namespace mmcl

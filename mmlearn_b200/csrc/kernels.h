@@ -30,7 +30,7 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
 // sim_fwd.cu, fused launches: fwd_begin, fwd_add_sub per (pair, direction[, key range]),
 // fwd_finish (CTA split + partial-statistics sizes), then fill the pointers and launch
 void fwd_begin(FwdLaunch* L, long long d);
-int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub);
+int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub, int phase);
 size_t fwd_finish(FwdLaunch* L, int num_sms, size_t* part_off_floats);
 int fwd_grid(const FwdLaunch& L);
 int fwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d);
@@ -115,6 +115,8 @@ cudaError_t launch_pack_rows_symm(const SymmArena* a, int world, int parity, con
                                   int src_dtype, long long src_rows, long long d,
                                   const int64_t* idx, long long n_out, int normalize,
                                   size_t off_rows, long long off_inv, cudaStream_t stream);
+cudaError_t debug_push(SymmArena* a, int world, int rank, int parity, size_t off, size_t bytes,
+                       int mode, int blocks, int threads, cudaStream_t stream);
 // Fences of different channels use different flag words and may overlap (different streams).
 cudaError_t launch_symm_fence(SymmArena* a, int world, int rank, cudaStream_t stream,
                               int channel = 0);

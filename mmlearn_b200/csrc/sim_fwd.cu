@@ -47,8 +47,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
@@ -119,9 +119,14 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const long long t_begin = (long long)blockIdx.x * L.tiles_per_cta;
-  long long t_end = t_begin + L.tiles_per_cta;
-  if (t_end > L.total_tiles) t_end = L.total_tiles;
+  // this CTA's share [t_begin, t_end) of phase ph
+  auto phase_range = [&](int ph, long long* t_begin, long long* t_end) {
+    const FwdPhase& P = L.phase[ph];
+    *t_begin = P.tile_begin + (long long)blockIdx.x * P.tiles_per_cta;
+    long long e = *t_begin + P.tiles_per_cta;
+    if (e > P.tile_begin + P.total) e = P.tile_begin + P.total;
+    *t_end = e;
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -130,6 +135,9 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       uint32_t phase = 0, qphase = 0;
       int seen_chan = -1;
       uint32_t seen = 0;
+      for (int ph = 0; ph < L.nphase; ++ph) {
+      long long t_begin, t_end;
+      phase_range(ph, &t_begin, &t_end);
       for (long long t = t_begin; t < t_end;) {
         si = find_sub(L, t, si);
         const FwdSub& S = L.sub[si];
@@ -183,6 +191,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         }
         t += j1 - j0;
       }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
@@ -191,6 +200,9 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       int stage = 0, si = 0;
       uint32_t phase = 0, qphase = 0;
       uint32_t acc = 0;
+      for (int ph = 0; ph < L.nphase; ++ph) {
+      long long t_begin, t_end;
+      phase_range(ph, &t_begin, &t_end);
       for (long long t = t_begin; t < t_end;) {
         si = find_sub(L, t, si);
         const int nkt_sub = L.sub[si].nkt_sub;
@@ -226,6 +238,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         if (kQRes) umma_commit(q_empty);
         t += j1 - j0;
       }
+      }
     }
   } else if (warp == 2 || warp == 3) {
     // ================================ peer pushes ==================================
@@ -256,26 +269,31 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
           }
         }
         if (sg.last_of_chan) {
-          // every lane: my stores are ordered before whatever I signal next
-          __threadfence_system();
+          // the warp's stores happen-before the barrier; lane 0's fence is cumulative over them
           __syncwarp();
+          int last = 0;
           if (lane == 0) {
+            __threadfence_system();
             const unsigned long long done = atomicAdd(L.tickets + sg.chan, 1ull) + 1ull;
-            if (done == L.ticket_target) {  // the last push warp of this launch for this channel
+            last = done == L.ticket_target ? 1 : 0;  // the last push warp of this launch
+            if (last) __threadfence_system();
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            if (sg.chan == L.status_chan && lane < L.world) {
+              unsigned long long sv = L.status_val;
+              for (int b = 0; b < L.nbad; ++b)
+                if (__ldcg(L.bad + b) == (unsigned long long)L.gen) sv &= ~1ull;
+              *reinterpret_cast<unsigned long long*>(L.peers[lane] + L.buf_off + L.status_off +
+                                                     8ull * L.rank) = sv;
+            }
+            // one lane per peer: fence + relaxed store = a release (eight release stores from one
+            // thread would serialise eight NVLink round trips)
+            if (lane < L.world) {
               __threadfence_system();
-              if (sg.chan == L.status_chan) {
-                unsigned long long sv = L.status_val;
-                for (int b = 0; b < L.nbad; ++b)
-                  if (__ldcg(L.bad + b) == (unsigned long long)L.gen) sv &= ~1ull;
-                for (int r = 0; r < L.world; ++r)
-                  *reinterpret_cast<unsigned long long*>(L.peers[r] + L.buf_off + L.status_off +
-                                                         8ull * L.rank) = sv;
-              }
-              __threadfence_system();
-              for (int r = 0; r < L.world; ++r)
-                st_release_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[r]) +
-                                       sg.chan * kMaxRanks + L.rank,
-                                   L.seq);
+              st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[lane]) +
+                                     sg.chan * kMaxRanks + L.rank,
+                                 L.seq);
             }
           }
           __syncwarp();
@@ -293,6 +311,9 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
     int si = 0;
     int kseen_chan = -1;
     uint32_t kseen = 0;
+    for (int ph = 0; ph < L.nphase; ++ph) {
+    long long t_begin, t_end;
+    phase_range(ph, &t_begin, &t_end);
     for (long long t = t_begin; t < t_end;) {
       si = find_sub(L, t, si);
       const FwdSub& S = L.sub[si];
@@ -492,8 +513,8 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       }
       }
       // partial statistics of this (sub-problem, q-tile, key range) segment
-      const long long first_tile = S.tile_begin + (long long)qt * S.nkt_sub;
-      const int c_first = int(first_tile / L.tiles_per_cta);
+      const long long first_tile = S.tile_begin - S.phase_begin + (long long)qt * S.nkt_sub;
+      const int c_first = int(first_tile / S.tpc);
       const int slot = 2 * (int(blockIdx.x) - c_first) + wg;  // one partial per column half
       const long long stride = (long long)S.nqt * BM;
       const long long o = (long long)slot * stride + (long long)qt * BM + row;
@@ -502,6 +523,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       S.part[2ll * S.max_slots * stride + o] = tt;
       t += j1 - j0;
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -509,25 +531,24 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
 }
 
 // Merge the per-CTA partial statistics of each row (single sub-problem launches of the ABI).
-__global__ void lse_combine_kernel(FwdSub S, int tiles_per_cta, float* __restrict__ lse,
-                                   float* __restrict__ esum) {
+__global__ void lse_combine_kernel(FwdSub S, float* __restrict__ lse, float* __restrict__ esum) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= S.nq) return;
   float M, Lsum, T;
-  fwd_combine_row(S, tiles_per_cta, row, &M, &Lsum, &T);
+  fwd_combine_row(S, row, &M, &Lsum, &T);
   const float sc = (*S.scale) * (S.qinv ? S.qinv[row] : 1.f);
   lse[row] = (M + log2f(Lsum)) * LN2;
   if (esum) esum[row] = sc * T / Lsum;
 }
 
 // Rank mode: total count of each row over the key segments of different CTAs.
-__global__ void rank_combine_kernel(FwdSub S, int tiles_per_cta, long long* __restrict__ rank) {
+__global__ void rank_combine_kernel(FwdSub S, long long* __restrict__ rank) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= S.nq) return;
   const int qt = row / BM;
-  const long long first_tile = S.tile_begin + (long long)qt * S.nkt_sub;
-  const int c_first = int(first_tile / tiles_per_cta);
-  const int c_last = int((first_tile + S.nkt_sub - 1) / tiles_per_cta);
+  const long long first_tile = S.tile_begin - S.phase_begin + (long long)qt * S.nkt_sub;
+  const int c_first = int(first_tile / S.tpc);
+  const int c_last = int((first_tile + S.nkt_sub - 1) / S.tpc);
   const long long stride = (long long)S.nqt * BM;
   long long total = 0;
   for (int s = 0; s < 2 * (c_last - c_first + 1); ++s)
@@ -542,6 +563,7 @@ __global__ void rank_combine_kernel(FwdSub S, int tiles_per_cta, long long* __re
 void fwd_begin(FwdLaunch* L, long long d) {
   *L = FwdLaunch();
   L->nsub = 0;
+  L->nphase = 0;
   L->total_tiles = 0;
   L->kchunks = int((d + BK - 1) / BK);
   L->world = 1;
@@ -551,8 +573,16 @@ void fwd_begin(FwdLaunch* L, long long d) {
   L->status_chan = -1;
 }
 
-int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub) {
-  if (L->nsub >= kMaxFwdSubs) return -1;
+// Sub-problems must be added in phase order (phase = 0, 0, ..., 1, 1, ...).
+int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub, int phase) {
+  if (L->nsub >= kMaxFwdSubs || phase < 0 || phase >= kMaxFwdPhases) return -1;
+  if (phase + 1 < L->nphase || phase > L->nphase) return -1;
+  if (phase == L->nphase) {
+    FwdPhase& P = L->phase[L->nphase++];
+    P.tile_begin = L->total_tiles;
+    P.total = 0;
+    P.tiles_per_cta = 1;
+  }
   FwdSub& S = L->sub[L->nsub];
   S = FwdSub();
   S.nq = int(nq);
@@ -562,9 +592,12 @@ int fwd_add_sub(FwdLaunch* L, long long nq, long long nk, int kt0, int nkt_sub) 
   S.kt0 = kt0;
   S.nkt_sub = nkt_sub < 0 ? S.nkt_all : nkt_sub;
   S.tile_begin = L->total_tiles;
+  S.phase_begin = L->phase[phase].tile_begin;
   S.label_off = -1;
   S.chan = kChanRows;
-  L->total_tiles += (long long)S.nqt * S.nkt_sub;
+  const long long tiles = (long long)S.nqt * S.nkt_sub;
+  L->total_tiles += tiles;
+  L->phase[phase].total += tiles;
   return L->nsub++;
 }
 
@@ -573,10 +606,16 @@ static size_t fwd_smem_budget() { return 227 * 1024 - 256 /*barriers*/ - 2 * BN 
 // Fixes the CTA split; returns the bytes of partial statistics the launch needs and the offset of
 // every sub-problem's partials inside that block (part_off[i], in floats).
 size_t fwd_finish(FwdLaunch* L, int num_sms, size_t* part_off) {
-  long long ctas = L->total_tiles < num_sms ? L->total_tiles : num_sms;
-  if (ctas < 1) ctas = 1;
-  L->tiles_per_cta = int((L->total_tiles + ctas - 1) / ctas);
-  if (L->tiles_per_cta < 1) L->tiles_per_cta = 1;
+  long long widest = 1;
+  for (int ph = 0; ph < L->nphase; ++ph)
+    if (L->phase[ph].total > widest) widest = L->phase[ph].total;
+  const long long ctas = widest < num_sms ? widest : num_sms;
+  L->ctas = int(ctas);
+  for (int ph = 0; ph < L->nphase; ++ph) {
+    FwdPhase& P = L->phase[ph];
+    P.tiles_per_cta = int((P.total + ctas - 1) / ctas);
+    if (P.tiles_per_cta < 1) P.tiles_per_cta = 1;
+  }
   const size_t budget = fwd_smem_budget();
   const bool qres = size_t(L->kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= budget;
   const size_t stage_bytes = qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
@@ -587,8 +626,10 @@ size_t fwd_finish(FwdLaunch* L, int num_sms, size_t* part_off) {
   size_t floats = 0;
   for (int i = 0; i < L->nsub; ++i) {
     FwdSub& S = L->sub[i];
+    for (int ph = 0; ph < L->nphase; ++ph)
+      if (S.phase_begin == L->phase[ph].tile_begin) S.tpc = L->phase[ph].tiles_per_cta;
     // x2: column halves; +1: a range may start inside the sub-problem's first CTA share
-    S.max_slots = 2 * ((S.nkt_sub + L->tiles_per_cta - 1) / L->tiles_per_cta + 1);
+    S.max_slots = 2 * ((S.nkt_sub + S.tpc - 1) / S.tpc + 1);
     if (part_off) part_off[i] = floats;
     floats += size_t(3) * S.max_slots * size_t(S.nqt) * BM;
   }
@@ -605,7 +646,7 @@ static cudaError_t launch_fwd(const TensorMaps& maps, const FwdLaunch& L, cudaSt
   const size_t stage_bytes = qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
   const size_t smem = (qres ? size_t(L.kchunks) * QCHUNK_BYTES : 0) + L.nstages * stage_bytes +
                       2 * BN * sizeof(float) + 256;
-  const int ctas = int((L.total_tiles + L.tiles_per_cta - 1) / L.tiles_per_cta);
+  const int ctas = L.ctas;
   cudaError_t e;
   if (qres) {
     e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true, kRank>,
@@ -622,9 +663,7 @@ static cudaError_t launch_fwd(const TensorMaps& maps, const FwdLaunch& L, cudaSt
   return cudaGetLastError();
 }
 
-int fwd_grid(const FwdLaunch& L) {
-  return int((L.total_tiles + L.tiles_per_cta - 1) / L.tiles_per_cta);
-}
+int fwd_grid(const FwdLaunch& L) { return L.ctas; }
 
 cudaError_t launch_fwd_fused(const TensorMaps& maps, const FwdLaunch& L, cudaStream_t stream) {
   if (L.total_tiles == 0) return cudaSuccess;
@@ -641,7 +680,7 @@ int fwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, lon
 size_t sim_lse_workspace_bytes(int num_sms, long long nq, long long nk, long long d) {
   FwdLaunch L;
   fwd_begin(&L, d);
-  fwd_add_sub(&L, nq, nk, 0, -1);
+  fwd_add_sub(&L, nq, nk, 0, -1, 0);
   return fwd_finish(&L, num_sms, nullptr);
 }
 
@@ -651,7 +690,7 @@ cudaError_t single_problem(int num_sms, const void* q, long long nq, const void*
                            long long d, void* workspace, size_t workspace_bytes, FwdLaunch* L,
                            TensorMaps* maps, const char** err, const char* who) {
   fwd_begin(L, d);
-  fwd_add_sub(L, nq, nk, 0, -1);
+  fwd_add_sub(L, nq, nk, 0, -1, 0);
   size_t off = 0;
   const size_t need = fwd_finish(L, num_sms, &off);
   if (workspace_bytes < need) {
@@ -685,8 +724,7 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
   L.sub[0].kinv = kinv;
   e = launch_fwd<false>(maps, L, stream);
   if (e != cudaSuccess) return e;
-  lse_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], L.tiles_per_cta, lse,
-                                                                    esum);
+  lse_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], lse, esum);
   count_launches(1);
   return cudaGetLastError();
 }
@@ -707,8 +745,7 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
   L.sub[0].tgt = tgt;
   e = launch_fwd<true>(maps, L, stream);
   if (e != cudaSuccess) return e;
-  rank_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], L.tiles_per_cta,
-                                                                     rank);
+  rank_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], rank);
   count_launches(1);
   return cudaGetLastError();
 }

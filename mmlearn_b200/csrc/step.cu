@@ -88,12 +88,15 @@ struct mmcl_step {
   // launch plans (shapes are fixed; pointers are filled in per call)
   FwdLaunch fwd;
   std::vector<size_t> fwd_part_off;
+  std::vector<int> sub_idx;  // [(pair * 2 + direction) * 2 + part]: forward sub-problem indices
+  int nsub_dir = 1;          // parts per (pair, direction): local keys [+ remote keys]
   BwdLaunch bwd;
   int post_blocks_per_pair = 0, post_main_blocks = 0, post_total_blocks = 0;
   std::vector<int> push_order;  // modalities in the order their rows are pushed to the peers
   // device state owned by the step: completion counters of the push warps / post-forward blocks
   unsigned long long* d_tickets = nullptr;  // [kFlagChannels] + [1]
-  unsigned long long n_push_launches = 0, n_post_launches = 0;
+  unsigned long long n_push_launches = 0, n_post_launches = 0, n_pack_launches = 0;
+  int first_wave = -1;  // modality the pack kernel itself stores into every rank (world > 1)
   unsigned gen = 0, salt = 0;
   unsigned long long seq = 0;  // flag sequence number of the last forward
   // verification
@@ -308,22 +311,38 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
     kt_hi = int((off + s->rows + 255) / 256);
   }
   const int n_local = kt_hi - kt_lo;
-  const int phases = (W > 1 && n_local < nkt_all) ? 2 : 1;
-  for (int ph = 0; ph < phases; ++ph)
-    for (int p = 0; p < s->P; ++p)
-      for (int dir = 0; dir < 2; ++dir) {
-        const int kt0 = ph == 0 ? kt_lo : kt_hi % nkt_all;
-        const int cnt = ph == 0 ? n_local : nkt_all - n_local;
-        if (fwd_add_sub(&s->fwd, s->rows, s->N, kt0, cnt) < 0) {
-          delete s;
-          return fail(MMCL_ERR_INVALID, "mmcl_step_create: too many forward sub-problems");
-        }
+  const bool split = W > 1 && n_local < nkt_all;
+  // phase 0: the local key block of every (pair, direction); phase 1: the remote keys of every
+  // pair's direction a (needs the peers' rows of the pairs' second modalities); phase 2: the
+  // remote keys of direction b.  world == 1: one phase with everything.
+  s->sub_idx.assign(size_t(s->P) * 4, -1);
+  s->nsub_dir = split ? 2 : 1;
+  bool plan_ok = true;
+  for (int p = 0; p < s->P && plan_ok; ++p)
+    for (int dir = 0; dir < 2; ++dir) {
+      const int k = fwd_add_sub(&s->fwd, s->rows, s->N, split ? kt_lo : 0, split ? n_local : -1, 0);
+      plan_ok = plan_ok && k >= 0;
+      s->sub_idx[(p * 2 + dir) * 2] = k;
+    }
+  if (split)
+    for (int dir = 0; dir < 2 && plan_ok; ++dir)
+      for (int p = 0; p < s->P; ++p) {
+        const int k = fwd_add_sub(&s->fwd, s->rows, s->N, kt_hi % nkt_all, nkt_all - n_local,
+                                  1 + dir);
+        plan_ok = plan_ok && k >= 0;
+        s->sub_idx[(p * 2 + dir) * 2 + 1] = k;
       }
+  if (!plan_ok) {
+    delete s;
+    return fail(MMCL_ERR_INVALID, "mmcl_step_create: too many forward sub-problems");
+  }
   s->fwd_part_off.assign(s->fwd.nsub, 0);
   s->fws_bytes = fwd_finish(&s->fwd, h->num_sms, s->fwd_part_off.data());
-  // modalities in the order the remote phase needs them as keys
-  for (int p = 0; p < s->P; ++p)
-    for (int m : {s->pairs[p].mod_b, s->pairs[p].mod_a}) {
+  // modalities in the order the remote phases need them as keys: the second modality of every
+  // pair (direction a), then the first ones (direction b), then whatever is left
+  for (int which = 0; which < 2; ++which)
+    for (int p = 0; p < s->P; ++p) {
+      const int m = which == 0 ? s->pairs[p].mod_b : s->pairs[p].mod_a;
       bool seen = false;
       for (int x : s->push_order) seen = seen || x == m;
       if (!seen) s->push_order.push_back(m);
@@ -333,6 +352,12 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
     for (int x : s->push_order) seen = seen || x == m;
     if (!seen) s->push_order.push_back(m);
   }
+
+  // The first modality of that order is needed before any remote tile can run: the pack kernel
+  // stores it into every rank at the full-GPU store rate (~550 GB/s measured at 8 GPUs); the
+  // others travel under the forward kernel's tensor-core work (its two spare warps per CTA
+  // sustain ~270 GB/s, enough to arrive before the phase that needs them).
+  s->first_wave = (W > 1 && s->push_order.size() > 1) ? s->push_order[0] : -1;
 
   // ---- backward plan ----
   bwd_begin(&s->bwd, s->d);
@@ -551,6 +576,21 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         pm.ids_dst = (W > 1 && s->is_key[m])
                          ? reinterpret_cast<int64_t*>(v.ar + s->ar_ids[m] + size_t(off) * 16)
                          : nullptr;
+        pm.fanout = m == s->first_wave ? 1 : 0;
+        pm.off_rows = s->ar_rows[m] + size_t(off) * d * 2;
+        pm.off_inv = s->ar_inv[m] + size_t(off) * 4;
+        pm.off_ids = s->ar_ids[m] + size_t(off) * 16;
+        pm.chan = row_chan(m);
+      }
+      if (W > 1) {
+        PL.world = W;
+        PL.rank = h->rank;
+        PL.peers = h->arena.d_peers;
+        PL.buf_off = buf_off(h, parity);
+        PL.tickets = s->d_tickets;
+        s->n_pack_launches += 1;
+        PL.ticket_target = s->n_pack_launches * (unsigned long long)((b + 7) / 8);
+        PL.seq = s->seq;
       }
       CU(launch_step_pack(PL, st), "mmcl_step_forward (pack)");
     }
@@ -562,13 +602,12 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
     {
       Range nv("mmcl.fwd");
       float* fws = reinterpret_cast<float*>(v.ws + s->off_fws);
-      const int phases = FL.nsub / (2 * s->P);
-      int k = 0;
-      for (int ph = 0; ph < phases; ++ph)
-        for (int p = 0; p < s->P; ++p) {
-          const mmcl_step_pair& pr = s->pairs[p];
-          float* vec = reinterpret_cast<float*>(v.ws + s->po[p].vec);
-          for (int dir = 0; dir < 2; ++dir, ++k) {
+      for (int p = 0; p < s->P; ++p) {
+        const mmcl_step_pair& pr = s->pairs[p];
+        float* vec = reinterpret_cast<float*>(v.ws + s->po[p].vec);
+        for (int dir = 0; dir < 2; ++dir)
+          for (int part = 0; part < s->nsub_dir; ++part) {
+            const int k = s->sub_idx[(p * 2 + dir) * 2 + part];
             const int mq = dir == 0 ? pr.mod_a : pr.mod_b;
             const int mk = dir == 0 ? pr.mod_b : pr.mod_a;
             FwdSub& S = FL.sub[k];
@@ -583,7 +622,7 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
             S.label_off = dir == 0 ? off : -1;
             S.pos = dir == 0 ? vec + 4 * b : nullptr;
           }
-        }
+      }
       FL.err = hdr + kHdrErr;
       if (W > 1) {
         FL.world = W;
@@ -611,13 +650,14 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         };
         for (size_t i = 0; i < s->push_order.size(); ++i) {
           const int m = s->push_order[i];
+          if (m == s->first_wave) continue;  // already in every rank's arena (pack kernel)
           const int ch = row_chan(m);
           // a channel shared by several modalities (m >= kMaxRowChannels) is released once, after
           // the last of them
           bool last_user = true;
           for (size_t j = i + 1; j < s->push_order.size(); ++j)
             if (row_chan(s->push_order[j]) == ch) last_user = false;
-          if (i == 0) FL.status_chan = ch;
+          if (FL.status_chan < 0) FL.status_chan = ch;
           if (s->is_key[m]) seg(s->ar_ids[m] + size_t(off) * 16, size_t(b) * 16, ch, 0);
           if (s->normalize) seg(s->ar_inv[m] + size_t(off) * 4, size_t(b) * 4, ch, 0);
           seg(s->ar_rows[m] + size_t(off) * d * 2, size_t(b) * d * 2, ch, last_user ? 1 : 0);
@@ -648,13 +688,13 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
       QL.ticket_target = s->n_post_launches * (unsigned long long)s->post_total_blocks;
       QL.seq = s->seq;
       bool any_lse = false;
-      const int phases = FL.nsub / (2 * s->P);
       for (int p = 0; p < s->P; ++p) {
         const mmcl_step_pair& pr = s->pairs[p];
         PostPair& pp = QL.pair[p];
         for (int dir = 0; dir < 2; ++dir) {
-          pp.nsub[dir] = phases;
-          for (int ph = 0; ph < phases; ++ph) pp.sub[dir][ph] = ph * 2 * s->P + 2 * p + dir;
+          pp.nsub[dir] = s->nsub_dir;
+          for (int part = 0; part < s->nsub_dir; ++part)
+            pp.sub[dir][part] = s->sub_idx[(p * 2 + dir) * 2 + part];
         }
         pp.vec = reinterpret_cast<float*>(v.ws + s->po[p].vec);
         pp.coef = pr.weight / (2.0 * pr.loss_rows);

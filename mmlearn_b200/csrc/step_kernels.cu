@@ -31,8 +31,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
@@ -115,6 +115,7 @@ __device__ __forceinline__ void store8(int odt, void* base, long long elem, cons
 
 // ------------------------------------------------------------------------------------------------
 __global__ void step_pack_kernel(const __grid_constant__ PackLaunch L) {
+  __shared__ int s_last;
   const int m = blockIdx.y;
   const PackMod& md = L.mod[m];
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -123,42 +124,72 @@ __global__ void step_pack_kernel(const __grid_constant__ PackLaunch L) {
     L.hdr[kHdrErr] = 0ull;
     L.hdr[kHdrVerify] = 0ull;
   }
-  if (row >= L.rows) return;
   const int d = L.d;
-  float inv = 1.f;
-  if (L.normalize) {
-    float ss = 0.f;
+  if (row < L.rows) {
+    float inv = 1.f;
+    if (L.normalize) {
+      float ss = 0.f;
+      for (int c = lane * 8; c < d; c += 256) {
+        float f[8];
+        load8(md.dtype, md.src, row * d + c, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+      }
+      ss = warp_sum(ss);
+      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+    }
     for (int c = lane * 8; c < d; c += 256) {
       float f[8];
       load8(md.dtype, md.src, row * d + c, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+      uint4 o;
+      o.x = bf16x2(f[0], f[1]);
+      o.y = bf16x2(f[2], f[3]);
+      o.z = bf16x2(f[4], f[5]);
+      o.w = bf16x2(f[6], f[7]);
+      if (md.fanout) {
+        for (int r = 0; r < L.world; ++r)
+          *reinterpret_cast<uint4*>(L.peers[r] + L.buf_off + md.off_rows + (size_t(row) * d + c) * 2) = o;
+      } else {
+        *reinterpret_cast<uint4*>(md.dst + row * d + c) = o;
+      }
     }
-    ss = warp_sum(ss);
-    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
-  }
-  for (int c = lane * 8; c < d; c += 256) {
-    float f[8];
-    load8(md.dtype, md.src, row * d + c, f);
-    uint4 o;
-    o.x = bf16x2(f[0], f[1]);
-    o.y = bf16x2(f[2], f[3]);
-    o.z = bf16x2(f[4], f[5]);
-    o.w = bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(md.dst + row * d + c) = o;
-  }
-  if (lane == 0) {
-    if (md.inv) md.inv[row] = inv;
     const longlong2 mine = __ldg(reinterpret_cast<const longlong2*>(md.ids) + row);
-    if (md.ids_dst) reinterpret_cast<longlong2*>(md.ids_dst)[row] = mine;
-    // every pair whose first modality this is: the local match is the identity only if the ids of
-    // both modalities agree row by row (distinctness is checked on the gathered key ids later)
-    for (int p = 0; p < L.P; ++p) {
-      if (L.pair_a[p] != m) continue;
-      const longlong2 other =
-          __ldg(reinterpret_cast<const longlong2*>(L.mod[L.pair_b[p]].ids) + row);
-      if (other.x != mine.x || other.y != mine.y) L.hdr[kHdrBad + p] = L.gen;
+    if (md.fanout) {
+      if (lane < L.world) {
+        char* base = L.peers[lane] + L.buf_off;
+        if (md.inv) reinterpret_cast<float*>(base + md.off_inv)[row] = inv;
+        if (md.ids_dst) reinterpret_cast<longlong2*>(base + md.off_ids)[row] = mine;
+      }
+    } else if (lane == 0) {
+      if (md.inv) md.inv[row] = inv;
+      if (md.ids_dst) reinterpret_cast<longlong2*>(md.ids_dst)[row] = mine;
     }
+    if (lane == 0) {
+      // every pair whose first modality this is: the local match is the identity only if the ids
+      // of both modalities agree row by row (distinctness is checked on the gathered key ids later)
+      for (int p = 0; p < L.P; ++p) {
+        if (L.pair_a[p] != m) continue;
+        const longlong2 other =
+            __ldg(reinterpret_cast<const longlong2*>(L.mod[L.pair_b[p]].ids) + row);
+        if (other.x != mine.x || other.y != mine.y) L.hdr[kHdrBad + p] = L.gen;
+      }
+    }
+  }
+  if (!md.fanout) return;
+  // last block of this modality: release its ready flags on every rank
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned long long done = atomicAdd(L.tickets + md.chan, 1ull) + 1ull;
+    s_last = done == L.ticket_target ? 1 : 0;
+    if (s_last) __threadfence_system();
+  }
+  __syncthreads();
+  if (s_last && int(threadIdx.x) < L.world) {
+    __threadfence_system();
+    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[threadIdx.x]) +
+                           md.chan * kMaxRanks + L.rank,
+                       L.seq);
   }
 }
 
@@ -221,7 +252,7 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
       for (int dir = 0; dir < 2; ++dir) {
         float M = -INFINITY, S = 0.f, T = 0.f;
         for (int k = 0; k < pp.nsub[dir]; ++k)
-          fwd_merge_row(F.sub[pp.sub[dir][k]], F.tiles_per_cta, int(row), &M, &S, &T);
+          fwd_merge_row(F.sub[pp.sub[dir][k]], int(row), &M, &S, &T);
         const FwdSub& s0 = F.sub[pp.sub[dir][0]];
         const float sc = (*s0.scale) * (s0.qinv ? s0.qinv[row] : 1.f);
         lse[dir] = (M + log2f(S)) * LN2;
@@ -272,9 +303,10 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
     }
   }
   // ---- last block: loss, verification word, log-sum-exp ready flags ----
-  __threadfence_system();
+  // (the block's peer stores happen-before the barrier; thread 0's fence is cumulative over them)
   __syncthreads();
   if (tid == 0) {
+    __threadfence_system();
     const unsigned long long done = atomicAdd(L.ticket, 1ull) + 1ull;
     s_last = done == L.ticket_target ? 1 : 0;
     if (s_last) __threadfence_system();
@@ -302,13 +334,14 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
       for (int r = 0; r < L.world; ++r) ok = ok && __ldcg(st + r) == L.status_ok;
     }
     L.hdr[kHdrVerify] = (static_cast<unsigned long long>(L.gen) << 1) | (ok ? 1ull : 0ull);
-    if (L.world > 1 && L.release_lse) {
-      __threadfence_system();
-      for (int r = 0; r < L.world; ++r)
-        st_release_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[r]) +
-                               kChanLse * kMaxRanks + L.rank,
-                           L.seq);
-    }
+  }
+  // log-sum-exp ready flags: one thread per peer (fence + relaxed store = a release; a release
+  // store per peer from one thread would serialise eight round trips)
+  if (L.world > 1 && L.release_lse && tid < L.world) {
+    __threadfence_system();
+    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[tid]) +
+                           kChanLse * kMaxRanks + L.rank,
+                       L.seq);
   }
 }
 
@@ -321,7 +354,7 @@ __global__ void step_motions_kernel(const __grid_constant__ MotionsLaunch L) {
     __threadfence_system();
     for (int c = 0; c < kFlagChannels; ++c)
       if ((L.chan_mask >> c) & 1u)
-        st_release_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[r]) + c * kMaxRanks + L.rank,
+        st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[r]) + c * kMaxRanks + L.rank,
                            L.seq);
     // nobody may overwrite the other parity buffer before every rank has left the previous step
     for (int c = 0; c < kFlagChannels; ++c)

@@ -20,6 +20,11 @@ struct PackMod {
   float* inv;              // this rank's slot of the inverse norms (null without l2_normalize)
   const int64_t* ids;      // [rows, 2]
   int64_t* ids_dst;        // this rank's slot of the gathered ids, or null
+  // first-wave modality (several ranks): the pack kernel itself stores rows / norms / ids into
+  // EVERY rank's arena (full-GPU store rate) and releases the modality's ready flags
+  int fanout;
+  unsigned long long off_rows, off_inv, off_ids;  // arena-buffer offsets of this rank's slots
+  int chan;
 };
 
 struct PackLaunch {
@@ -28,6 +33,13 @@ struct PackLaunch {
   unsigned gen;
   unsigned long long* hdr;
   int pair_a[kStepMaxPairs], pair_b[kStepMaxPairs];
+  // fan-out of first-wave modalities
+  int world, rank;
+  char* const* peers;
+  unsigned long long buf_off;
+  unsigned long long* tickets;        // [kFlagChannels]
+  unsigned long long ticket_target;   // pack launches so far x blocks per modality
+  unsigned long long seq;
   PackMod mod[kStepMaxMods];
 };
 

@@ -309,6 +309,48 @@ cudaError_t launch_pack_rows_symm(const SymmArena* a, int world, int parity, con
   return cudaGetLastError();
 }
 
+// Diagnostic (tools/push_bench.py): the same bytes pushed three ways, to pick the transport.
+//   mode 0: store kernel with a caller-chosen grid (how many threads does NVLink need?)
+//   mode 1: one cudaMemcpyAsync per peer on `stream` (copy engines, serial)
+//   mode 2: one cudaMemcpyAsync per peer on per-peer side streams (copy engines, parallel)
+cudaError_t debug_push(SymmArena* a, int world, int rank, int parity, size_t off, size_t bytes,
+                       int mode, int blocks, int threads, cudaStream_t stream) {
+  const size_t base = kFlagBytes + size_t(parity & 1) * a->bytes + off;
+  if (mode == 0) {
+    symm_put_kernel<uint4><<<blocks, threads, 0, stream>>>(
+        a->d_peers, world, base, reinterpret_cast<const uint4*>(a->local + base), bytes / 16, rank);
+    count_launches(1);
+    return cudaGetLastError();
+  }
+  static cudaStream_t side[kMaxRanks] = {};
+  static cudaEvent_t ev_fork = nullptr, ev_join[kMaxRanks] = {};
+  cudaError_t e = cudaSuccess;
+  if (mode == 2) {
+    if (!ev_fork) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_fork, stream);
+  }
+  for (int r = 0; r < world && e == cudaSuccess; ++r) {
+    if (r == rank) continue;
+    cudaStream_t st = stream;
+    if (mode == 2) {
+      if (!side[r]) {
+        e = cudaStreamCreateWithFlags(&side[r], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join[r], cudaEventDisableTiming);
+        if (e != cudaSuccess) break;
+      }
+      st = side[r];
+      e = cudaStreamWaitEvent(st, ev_fork, 0);
+      if (e != cudaSuccess) break;
+    }
+    e = cudaMemcpyAsync(a->peers[r] + base, a->local + base, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && mode == 2) {
+      e = cudaEventRecord(ev_join[r], st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ev_join[r], 0);
+    }
+  }
+  return e;
+}
+
 cudaError_t launch_symm_fence(SymmArena* a, int world, int rank, cudaStream_t stream,
                               int channel) {
   if (channel < 0 || channel >= kFenceChannels || world > kMaxRanks) return cudaErrorInvalidValue;

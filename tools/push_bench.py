@@ -82,7 +82,19 @@ def f(parity):
     check(lib.mmcl_symm_fence(h, st), "fence")
 
 
+def push(mode, blocks=0, threads=0):
+    def run(parity):
+        check(lib.mmcl_debug_push(h, parity, off_rows + rank * rows * d * 2, rows * d * 2, mode, blocks,
+                                  threads, st), "push")
+        check(lib.mmcl_symm_fence(h, st), "fence")
+    return run
+
+
 timed(f, "fence alone")
+for blocks, threads in ((148, 64), (148, 128), (148, 256), (296, 256), (592, 256), (1184, 256)):
+    timed(push(0, blocks, threads), f"store kernel {blocks}x{threads} + fence")
+timed(push(1), "cudaMemcpyAsync per peer, 1 stream")
+timed(push(2), "cudaMemcpyAsync per peer, side streams")
 timed(a, "pack_rows_symm + fence")
 timed(b, "symm_put + fence")
 timed(c, "NCCL all-gather (in place)")
