@@ -182,6 +182,17 @@ int mmcl_sim_rank_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void
                       const float* thr, const int64_t* skip, int64_t* rank, void* workspace,
                       size_t workspace_bytes, mmcl_stream stream);
 
+/* Zero-shot classification scores on the same mainloop:
+ *   out[i, j] = scale * qinv_i * kinv_j * (q_i . k_j)      fp32 [nq, out_ld], out_ld >= nk
+ * (q = query embeddings, k = class embeddings; scale = 100 in the reference).  Unlike the loss,
+ * the scores are needed by the caller's metric collection, so they are stored; the top-k
+ * accuracies alone come from mmcl_sim_rank_fwd without storing anything.
+ * Replaces: `100.0 * _safe_matmul(query_embeddings, class_embeddings)`
+ * (mmlearn/tasks/zero_shot_classification.py:209-214). */
+int mmcl_sim_logits_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                        int64_t nk, int64_t d, double scale, const float* qinv, const float* kinv,
+                        float* out, int64_t out_ld, mmcl_stream stream);
+
 /* Caller glue of the task: log_scale[i] <- clamp(log_scale[i], 0,
  * log(max_scale)) IN PLACE and scale_out[i] = exp(log_scale[i]), one launch.
  * Replaces: `self.log_logit_scale.clamp_(0, math.log(self.max_logit_scale))` followed by

@@ -8,6 +8,8 @@ Public surface (mirrors the reference for this path only):
 * :func:`find_matching_indices` -- device version of the reference function
 * :class:`RetrievalRecallAtK` -- drop-in for ``mmlearn.modules.metrics.RetrievalRecallAtK`` on the
   same similarity mainloop
+* :class:`ZeroShotScores` -- the scoring step of ``mmlearn.tasks.ZeroShotClassification`` (scores
+  and top-k ranks of queries against class embeddings) on that mainloop
 
 Everything computes through ``libmmcl.so`` (``include/mmcl.h``); there is no CPU fallback.
 """
@@ -17,6 +19,7 @@ from .loss import ContrastiveLoss, FusedContrastiveLoss, find_matching_indices, 
 from .modalities import LossPairSpec, Modalities
 from .plan import PairPlan
 from .retrieval import RetrievalRecallAtK
+from .zero_shot import ZeroShotScores
 
 __all__ = [
     "ContrastiveLoss",
@@ -25,6 +28,7 @@ __all__ = [
     "Modalities",
     "PairPlan",
     "RetrievalRecallAtK",
+    "ZeroShotScores",
     "find_matching_indices",
     "get_handle",
 ]

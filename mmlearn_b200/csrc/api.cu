@@ -428,6 +428,23 @@ int mmcl_sim_rank_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void
   return MMCL_OK;
 }
 
+int mmcl_sim_logits_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16,
+                        int64_t nk, int64_t d, double scale, const float* qinv, const float* kinv,
+                        float* out, int64_t out_ld, mmcl_stream stream) {
+  REQUIRE(h, "mmcl_sim_logits_fwd: null handle");
+  int rc = check_sim_args("mmcl_sim_logits_fwd", q_bf16, nq, k_bf16, nk, d);
+  if (rc) return rc;
+  if (nq == 0 || nk == 0) return MMCL_OK;
+  REQUIRE(out && out_ld >= nk, "mmcl_sim_logits_fwd: null output / row pitch smaller than nk");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const char* err = nullptr;
+  cudaError_t e = launch_sim_logits_fwd(h->num_sms, q_bf16, nq, k_bf16, nk, d, float(scale), qinv,
+                                        kinv, out, out_ld, static_cast<cudaStream_t>(stream), &err);
+  if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_logits_fwd");
+  return MMCL_OK;
+}
+
 int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const float* esum_a,
                    const float* esum_b, const float* pos, int64_t n, double weight, double n_norm,
                    const float* scale, float* out2, mmcl_stream stream) {

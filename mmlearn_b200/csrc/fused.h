@@ -45,6 +45,9 @@ struct FwdSub {  // one direction of one pair, restricted to a rotated range of 
   float* pos;                 // [nq] positive logits (written by the tile that holds them) or null
   const float* thr;           // rank mode
   const long long* tgt;       // rank mode
+  float* out;                 // store mode: [nq, out_ld] fp32 logits
+  long long out_ld;
+  float out_scale;
 };
 
 constexpr int kMaxPushSegs = 16;
@@ -114,6 +117,11 @@ struct BwdProb {  // one side of one pair: dX = sum_j G_ij yinv_j Y_j
   const float* off_col;
   float off_mul, row_add, col_add;
   float* dx;             // [nx, d] fp32
+  // (min, max) of the raw row offsets and, per rank, of the raw column offsets, when the caller
+  // already knows them (the step's post-forward kernel does); null: the kernel scans the vectors
+  const float* rng_row;  // [2]
+  const float* rng_col;  // [rng_col_count][rng_col_stride floats], (min, max) first
+  int rng_col_stride, rng_col_count;
 };
 
 struct BwdLaunch {

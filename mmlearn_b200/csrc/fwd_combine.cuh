@@ -21,14 +21,30 @@ __device__ __forceinline__ void fwd_merge_row(const FwdSub& S, int row, float* M
   const float* pl = S.part + (long long)S.max_slots * stride;
   const float* pt = S.part + 2ll * S.max_slots * stride;
   float m = *M, l = *L, t = *T;
-  for (int s = 0; s < nslots; ++s) {
-    const long long o = (long long)s * stride + row;
-    const float ms = pm[o];
-    const float mn = fmaxf(m, ms);
+  // batches of four slots: twelve independent loads in flight, then the (sequential) merge
+  for (int s0 = 0; s0 < nslots; s0 += 4) {
+    float ms[4], ls[4], ts[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool ok = s0 + k < nslots;
+      const long long o = (long long)(ok ? s0 + k : s0) * stride + row;
+      ms[k] = ok ? __ldcg(pm + o) : -INFINITY;
+      ls[k] = ok ? __ldcg(pl + o) : 0.f;
+      ts[k] = ok ? __ldcg(pt + o) : 0.f;
+    }
+    float mn = m;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mn = fmaxf(mn, ms[k]);
     if (mn == -INFINITY) continue;  // nothing seen so far
-    const float a = exp2f(m - mn), b = exp2f(ms - mn);
-    l = l * a + pl[o] * b;
-    t = t * a + pt[o] * b;
+    const float a = exp2f(m - mn);
+    l *= a;
+    t *= a;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float b = exp2f(ms[k] - mn);
+      l = fmaf(ls[k], b, l);
+      t = fmaf(ts[k], b, t);
+    }
     m = mn;
   }
   *M = m;

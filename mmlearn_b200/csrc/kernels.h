@@ -27,6 +27,11 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
                                 void* workspace, size_t workspace_bytes, cudaStream_t stream,
                                 const char** err);
 
+cudaError_t launch_sim_logits_fwd(int num_sms, const void* q, long long nq, const void* k,
+                                  long long nk, long long d, float scale, const float* qinv,
+                                  const float* kinv, float* out, long long out_ld,
+                                  cudaStream_t stream, const char** err);
+
 // sim_fwd.cu, fused launches: fwd_begin, fwd_add_sub per (pair, direction[, key range]),
 // fwd_finish (CTA split + partial-statistics sizes), then fill the pointers and launch
 void fwd_begin(FwdLaunch* L, long long d);

@@ -148,13 +148,13 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
   uint64_t* full = bars;                  // [NSTAGES] TMA -> MMA
   uint64_t* empty = bars + NSTAGES;       // [NSTAGES] MMA -> TMA
   uint64_t* s_full = bars + 2 * NSTAGES;  // S tile complete in tensor memory
-  uint64_t* g_full = s_full + 1;          // [2] own G, key half 0 / 1, written to tensor memory
-  uint64_t* stg_full = s_full + 3;        // partner's G has landed in my staging buffer
-  uint64_t* stg_free = s_full + 4;        // the partner has consumed what I stored in ITS staging
-  uint64_t* acc_full = s_full + 5;
-  uint64_t* acc_empty = s_full + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
-  float* s_range = reinterpret_cast<float*>(s_full + 8);  // [16] lo per warp, [16] hi per warp
+  uint64_t* g_full = s_full + 1;          // [4] own G, 64-key quarter q, written to tensor memory
+  uint64_t* stg_full = s_full + 5;        // partner's G has landed in my staging buffer
+  uint64_t* stg_free = s_full + 6;        // the partner has consumed what I stored in ITS staging
+  uint64_t* acc_full = s_full + 7;
+  uint64_t* acc_empty = s_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 9);
+  float* s_range = reinterpret_cast<float*>(s_full + 10);  // [16] lo per warp, [16] hi per warp
   float* s_mu = s_range + 32;                              // [kMaxBwdProbs] centre of the offsets
   int* s_fast = reinterpret_cast<int*>(s_mu + kMaxBwdProbs);  // [kMaxBwdProbs] one-exponential form
 
@@ -169,8 +169,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       mbar_init(&empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(&g_full[0], 256);
-    mbar_init(&g_full[1], 256);
+    for (int i = 0; i < 4; ++i) mbar_init(&g_full[i], 256);
     mbar_init(stg_full, 1);  // armed with expect_tx by the MMA issuer; bytes arrive via st.async
     mbar_init(stg_free, 1);
     mbar_init(acc_full, 1);
@@ -198,14 +197,31 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       if (threadIdx.x == 0) { s_mu[pi] = 0.f; s_fast[pi] = 0; }
       continue;
     }
+    if (p.rng_row && p.rng_col) {
+      // the caller supplies the ranges (the scan below costs ~N/384 dependent L2 round trips)
+      if (threadIdx.x == 0) {
+        float l2 = fmaf(__ldcg(p.rng_row), p.off_mul, p.row_add);
+        float h2 = fmaf(__ldcg(p.rng_row + 1), p.off_mul, p.row_add);
+        for (int r = 0; r < p.rng_col_count; ++r) {
+          const float* q = p.rng_col + (long long)r * p.rng_col_stride;
+          l2 = fminf(l2, fmaf(__ldcg(q), p.off_mul, p.col_add));
+          h2 = fmaxf(h2, fmaf(__ldcg(q + 1), p.off_mul, p.col_add));
+        }
+        s_mu[pi] = 0.5f * (l2 + h2);
+        s_fast[pi] = (h2 - l2) <= 2.f * kFastRange ? 1 : 0;
+      }
+      continue;
+    }
+    // (scan path: callers without precomputed ranges order the vectors before the launch, so
+    // plain cached loads are safe here)
     float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < p.nx; i += NTHREADS) {
-      const float v = fmaf(__ldcg(p.off_row + i), p.off_mul, p.row_add);
+      const float v = fmaf(p.off_row[i], p.off_mul, p.row_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
     for (int i = threadIdx.x; i < p.ny; i += NTHREADS) {
-      const float v = fmaf(__ldcg(p.off_col + i), p.off_mul, p.col_add);
+      const float v = fmaf(p.off_col[i], p.off_mul, p.col_add);
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
@@ -230,6 +246,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     }
     __syncthreads();
   }
+  __syncthreads();
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -330,11 +347,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       auto issue_dx_own = [&]() {  // A = own G in tensor memory
         begin_dx();
         for (int js = 0; js < BNY / 64; ++js) {
-          if ((js & 1) == 0) {
-            mbar_wait(&g_full[js >> 1], own_cnt & 1);
-            tc_fence_after();
-            TRACE(5 + (js >> 1), own_cnt);
-          }
+          mbar_wait(&g_full[js], own_cnt & 1);
+          tc_fence_after();
+          if ((js & 1) == 0) TRACE(5 + (js >> 1), own_cnt);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
@@ -462,8 +477,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         // on its staging buffer; nothing is read here, so CTA-scope acquire is enough)
         mbar_wait(stg_free, (own_cnt & 1) ^ 1);
         if (lane == 0 && q == 0) TRACE(12 + wg, own_cnt);
-        // both warpgroups convert key half 0 first (chunks 0,1 | 2,3), then half 1 (4,5 | 6,7), so
-        // the dX MMAs of half 0 run under the conversion of half 1
+        // Conversion order: step ci converts the 64-key quarter ci (32-column chunk 2*ci by
+        // warpgroup 0, chunk 2*ci+1 by warpgroup 1) and hands it to the MMA issuer at once, so the
+        // dX MMAs of quarter ci run under the conversion of the quarters after it.
         // Software pipeline over 16-column halves: the tensor-memory load of the next half is
         // in flight while the current one is converted.
         uint32_t va[16], vb[16], g[16];
@@ -478,18 +494,15 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           else
             conv16<2>(v, gout, cc, offr, sCol + col);
         };
-        tmem_ld_x16(sbase + uint32_t(wg * 2) * 32u, va);
+        tmem_ld_x16(sbase + uint32_t(wg) * 32u, va);
 #pragma unroll 1
         for (int ci = 0; ci < 4; ++ci) {
-          const int ch = (ci >> 1) * 4 + wg * 2 + (ci & 1);
+          const int ch = ci * 2 + wg;
           tmem_ld_wait();
           tmem_ld_x16(sbase + ch * 32 + 16, vb);
           convert(va, g, ch * 32);
           tmem_ld_wait();
-          if (ci < 3) {
-            const int chn = ((ci + 1) >> 1) * 4 + wg * 2 + ((ci + 1) & 1);
-            tmem_ld_x16(sbase + chn * 32, va);
-          }
+          if (ci < 3) tmem_ld_x16(sbase + ((ci + 1) * 2 + wg) * 32, va);
           convert(vb, g + 8, ch * 32 + 16);
           // G chunk ch overwrites the first 16 columns of S chunk ch (already consumed by this
           // very thread), so no other warp's reads are ever at risk
@@ -524,11 +537,10 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
             st_async_v4(abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4), w0, w1, w2, w3,
                         peer_stg_full);
           }
-          if (ci & 1) {  // this warpgroup's share of key half ci/2 is in tensor memory
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&g_full[ci >> 1]);
-          }
+          // this warpgroup's share of quarter ci is in tensor memory
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&g_full[ci]);
         }
         if (lane == 0 && q == 0) TRACE(14 + wg, own_cnt);
         ++own_cnt;

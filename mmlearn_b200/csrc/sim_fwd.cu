@@ -77,10 +77,12 @@ __device__ __forceinline__ int find_sub(const FwdLaunch& L, long long t, int s) 
   return s;
 }
 
-// kRank == false: online log-sum-exp epilogue (the loss).  kRank == true: the same mainloop with a
+// kMode == 0: online log-sum-exp epilogue (the loss).  kMode == 2: the logits themselves are
+// stored, out[i, j] = out_scale * qinv_i * kinv_j * (q_i . k_j) (zero-shot classification scores:
+// few keys, every score needed by the metric collection).  kMode == 1: the same mainloop with a
 // counting epilogue -- per row, the number of keys whose similarity exceeds the row's threshold
 // (retrieval rank of the positive, mmcl_sim_rank_fwd); one multiply + compare per logit, no MUFU.
-template <bool kQRes, bool kRank>
+template <bool kQRes, int kMode>
 __global__ void __launch_bounds__(384, 1)
 sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ FwdLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -323,7 +325,8 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       if (j1 > S.nkt_sub) j1 = S.nkt_sub;
       const float* kinv = S.kinv;
       const int nk = S.nk;
-      const float s = kRank ? 1.f : *S.scale;
+      constexpr bool kRank = kMode == 1;
+      const float s = kMode == 0 ? *S.scale : 1.f;
       const bool neg = s < 0.f;
       float m = -INFINITY, l = 0.f, tt = 0.f;
       const int grow = qt * BM + row;
@@ -352,6 +355,42 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         return __ldcg(kinv + gk);
       };
       float knext = key_factor(tile_of(j0));  // prefetched one tile ahead
+      if (kMode == 2) {
+        const float cq = S.out_scale * ((S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f);
+        for (int j = j0; j < j1; ++j) {
+          const int kt = tile_of(j);
+          const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
+          float* kv = sKinv + ab * BN;
+          kv[et] = knext;
+          if (j + 1 < j1) knext = key_factor(tile_of(j + 1));
+          named_bar_sync(1, 256);
+          mbar_wait(&acc_full[ab], aphase);
+          tc_fence_after();
+          const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
+          const int valid = nk - kt * BN;
+#pragma unroll 1
+          for (int ch = ch0; ch < ch0 + BN / 64; ++ch) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            if (ch == ch0 + BN / 64 - 1) {
+              tc_fence_before();
+              mbar_arrive(&acc_empty[ab]);
+            }
+            const int cv = valid - ch * 32;
+            if (grow < S.nq && cv > 0) {
+              const float* kc = kv + ch * 32;
+              float* dst = S.out + (long long)grow * S.out_ld + (long long)kt * BN + ch * 32;
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (e < cv) dst[e] = __uint_as_float(v[e]) * kc[e] * cq;
+            }
+          }
+          ++acc;
+        }
+        t += j1 - j0;
+        continue;  // nothing to merge afterwards
+      }
       if (kRank) {
         // count_j [ qinv_i * kinv_j * (q_i . k_j) > thr_i ]  ==  [ x_ij * kinv_j > thr_i / qinv_i ]
         const float qi = (S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f;
@@ -640,7 +679,7 @@ static bool fwd_qres(const FwdLaunch& L) {
   return size_t(L.kchunks) * QCHUNK_BYTES + 3 * size_t(KCHUNK_BYTES) <= fwd_smem_budget();
 }
 
-template <bool kRank>
+template <int kMode>
 static cudaError_t launch_fwd(const TensorMaps& maps, const FwdLaunch& L, cudaStream_t stream) {
   const bool qres = fwd_qres(L);
   const size_t stage_bytes = qres ? KCHUNK_BYTES : QCHUNK_BYTES + KCHUNK_BYTES;
@@ -649,15 +688,15 @@ static cudaError_t launch_fwd(const TensorMaps& maps, const FwdLaunch& L, cudaSt
   const int ctas = L.ctas;
   cudaError_t e;
   if (qres) {
-    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true, kRank>,
+    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<true, kMode>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<true, kRank><<<ctas, 384, smem, stream>>>(maps, L);
+    sim_lse_fwd_kernel<true, kMode><<<ctas, 384, smem, stream>>>(maps, L);
   } else {
-    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false, kRank>,
+    e = cudaFuncSetAttribute(sim_lse_fwd_kernel<false, kMode>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    sim_lse_fwd_kernel<false, kRank><<<ctas, 384, smem, stream>>>(maps, L);
+    sim_lse_fwd_kernel<false, kMode><<<ctas, 384, smem, stream>>>(maps, L);
   }
   count_launches(1);
   return cudaGetLastError();
@@ -667,7 +706,7 @@ int fwd_grid(const FwdLaunch& L) { return L.ctas; }
 
 cudaError_t launch_fwd_fused(const TensorMaps& maps, const FwdLaunch& L, cudaStream_t stream) {
   if (L.total_tiles == 0) return cudaSuccess;
-  return launch_fwd<false>(maps, L, stream);
+  return launch_fwd<0>(maps, L, stream);
 }
 
 int fwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d) {
@@ -722,7 +761,7 @@ cudaError_t launch_sim_lse_fwd(int num_sms, const void* q, long long nq, const v
   L.sub[0].scale = scale;
   L.sub[0].qinv = qinv;
   L.sub[0].kinv = kinv;
-  e = launch_fwd<false>(maps, L, stream);
+  e = launch_fwd<0>(maps, L, stream);
   if (e != cudaSuccess) return e;
   lse_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], lse, esum);
   count_launches(1);
@@ -743,11 +782,35 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
   L.sub[0].kinv = kinv;
   L.sub[0].thr = thr;
   L.sub[0].tgt = tgt;
-  e = launch_fwd<true>(maps, L, stream);
+  e = launch_fwd<1>(maps, L, stream);
   if (e != cudaSuccess) return e;
   rank_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], rank);
   count_launches(1);
   return cudaGetLastError();
+}
+
+cudaError_t launch_sim_logits_fwd(int num_sms, const void* q, long long nq, const void* k,
+                                  long long nk, long long d, float scale, const float* qinv,
+                                  const float* kinv, float* out, long long out_ld,
+                                  cudaStream_t stream, const char** err) {
+  FwdLaunch L;
+  TensorMaps maps;
+  fwd_begin(&L, d);
+  fwd_add_sub(&L, nq, nk, 0, -1, 0);
+  fwd_finish(&L, num_sms, nullptr);
+  if (make_tmap_bf16_sw128(&maps.tm[0], q, nq, d, d, BM) ||
+      make_tmap_bf16_sw128(&maps.tm[1], k, nk, d, d, BN)) {
+    *err = "sim_logits_fwd: cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  L.sub[0].map_q = 0;
+  L.sub[0].map_k = 1;
+  L.sub[0].qinv = qinv;
+  L.sub[0].kinv = kinv;
+  L.sub[0].out = out;
+  L.sub[0].out_ld = out_ld;
+  L.sub[0].out_scale = scale;
+  return launch_fwd<2>(maps, L, stream);
 }
 
 }  // namespace mmcl

@@ -53,6 +53,8 @@ struct PairOff {
   size_t vec;         // workspace: 5 x rows floats
   size_t dacc[2];     // workspace: rows x d floats (or SIZE_MAX)
   size_t lse_all[2];  // arena: N floats each (world > 1, need_grad, has_col)
+  size_t range;       // workspace: (min, max) of lse_a, lse_b of this rank (4 floats)
+  size_t range_all;   // arena: [world][4] floats
 };
 
 struct Range {
@@ -78,7 +80,7 @@ struct mmcl_step {
   std::vector<char> is_key;  // modality is the second entry of some pair (its ids are checked)
   bool pair_bwd = false;     // the CTA-pair backward kernel supports this d
   // workspace layout
-  size_t off_out2 = 0, off_blk = 0, off_fws = 0, fws_bytes = 0, off_scratch = 0, ws_bytes = 0;
+  size_t off_out2 = 0, off_blk = 0, off_blkr = 0, off_fws = 0, fws_bytes = 0, off_scratch = 0, ws_bytes = 0;
   std::vector<size_t> ws_rows, ws_inv, ws_idtab;
   unsigned long long idtab_size = 0;
   std::vector<PairOff> po;
@@ -201,6 +203,18 @@ int enqueue_grad_kernels(mmcl_step* s, const float* scales, const Views& v, int 
         q.row_add = float(log2(pr.row_den));
         q.col_add = q.off_col ? float(log2(pr.col_den)) : 0.f;
         q.dx = reinterpret_cast<float*>(v.ws + s->po[p].dacc[side]);
+        // offset ranges from the post-forward kernel (own rows: this rank's; columns: every rank's)
+        const float* rng = reinterpret_cast<const float*>(v.ws + s->po[p].range);
+        q.rng_row = rng + 2 * side;
+        if (q.off_col && h->world > 1) {
+          q.rng_col = reinterpret_cast<const float*>(v.ar + s->po[p].range_all) + 2 * (1 - side);
+          q.rng_col_stride = 4;
+          q.rng_col_count = h->world;
+        } else {
+          q.rng_col = rng + 2 * (1 - side);
+          q.rng_col_stride = 4;
+          q.rng_col_count = 1;
+        }
       }
     }
     if (k == 0) return MMCL_OK;
@@ -386,6 +400,13 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
   s->post_main_blocks = s->post_blocks_per_pair * s->P;
   s->off_blk = o;
   o = align_up(o + size_t(s->post_main_blocks) * 16);
+  s->off_blkr = o;
+  o = align_up(o + size_t(s->post_main_blocks) * 16);
+  for (int p = 0; p < s->P; ++p) {
+    s->po[p].range = o;
+    o += 16;
+  }
+  o = align_up(o);
   s->idtab_size = 4 * next_pow2(2 * (W > 1 ? N : b));
   s->ws_idtab.assign(s->M, 0);
   int nkeys = 0;
@@ -445,6 +466,10 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
         s->po[p].lse_all[side] = a;
         if (s->need_grad && s->pairs[p].has_col) a = align_up(a + N * 4);
       }
+    for (int p = 0; p < s->P; ++p) {
+      s->po[p].range_all = a;
+      a = align_up(a + size_t(W) * 16);
+    }
     s->ar_bytes = a;
   }
   // ---- device counters + verification state ----
@@ -682,6 +707,7 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
       QL.gen = gen;
       QL.hdr = hdr;
       QL.blk_part = reinterpret_cast<double*>(v.ws + s->off_blk);
+      QL.blk_range = reinterpret_cast<float*>(v.ws + s->off_blkr);
       QL.out2 = out2;
       QL.ticket = s->d_tickets + kFlagChannels;
       s->n_post_launches += 1;
@@ -702,6 +728,8 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         pp.push_lse = (W > 1 && s->need_grad && pr.has_col) ? 1 : 0;
         pp.lse_off[0] = s->po[p].lse_all[0];
         pp.lse_off[1] = s->po[p].lse_all[1];
+        pp.range = reinterpret_cast<float*>(v.ws + s->po[p].range);
+        pp.range_off = s->po[p].range_all;
         any_lse = any_lse || pp.push_lse;
       }
       if (W > 1) {

@@ -238,6 +238,7 @@ __device__ void id_insert(const PostIds& I, long long j, unsigned gen, unsigned 
 __global__ void __launch_bounds__(256)
 step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant__ PostLaunch L) {
   __shared__ double sh[2][8];
+  __shared__ float shr[4][8];
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (int(blockIdx.x) < L.main_blocks) {
@@ -246,6 +247,7 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
     const long long row = (long long)(blockIdx.x % L.blocks_per_pair) * 256 + tid;
     const PostPair& pp = L.pair[p];
     double lterm = 0.0, eterm = 0.0;
+    float rmin[2] = {INFINITY, INFINITY}, rmax[2] = {-INFINITY, -INFINITY};
     if (row < L.rows) {
       float lse[2], es[2];
 #pragma unroll
@@ -260,6 +262,8 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
       }
       float* vec = pp.vec;
       const float pos = vec[4 * L.rows + row];
+      rmin[0] = rmax[0] = lse[0];
+      rmin[1] = rmax[1] = lse[1];
       vec[row] = lse[0];
       vec[L.rows + row] = lse[1];
       vec[2 * L.rows + row] = es[0];
@@ -280,13 +284,31 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
       lterm += __shfl_xor_sync(0xffffffffu, lterm, o);
       eterm += __shfl_xor_sync(0xffffffffu, eterm, o);
     }
-    if (lane == 0) { sh[0][w] = lterm; sh[1][w] = eterm; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        rmin[k] = fminf(rmin[k], __shfl_xor_sync(0xffffffffu, rmin[k], o));
+        rmax[k] = fmaxf(rmax[k], __shfl_xor_sync(0xffffffffu, rmax[k], o));
+      }
+    if (lane == 0) {
+      sh[0][w] = lterm;
+      sh[1][w] = eterm;
+      shr[0][w] = rmin[0]; shr[1][w] = rmax[0]; shr[2][w] = rmin[1]; shr[3][w] = rmax[1];
+    }
     __syncthreads();
     if (tid == 0) {
       double l = 0.0, e = 0.0;
-      for (int i = 0; i < 8; ++i) { l += sh[0][i]; e += sh[1][i]; }
+      float r4[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+      for (int i = 0; i < 8; ++i) {
+        l += sh[0][i];
+        e += sh[1][i];
+        r4[0] = fminf(r4[0], shr[0][i]); r4[1] = fmaxf(r4[1], shr[1][i]);
+        r4[2] = fminf(r4[2], shr[2][i]); r4[3] = fmaxf(r4[3], shr[3][i]);
+      }
       L.blk_part[2 * blockIdx.x] = l;
       L.blk_part[2 * blockIdx.x + 1] = e;
+      for (int k = 0; k < 4; ++k) L.blk_range[4 * blockIdx.x + k] = r4[k];
     }
   } else {
     // ---- distinctness of the (gathered) key ids ----
@@ -313,17 +335,58 @@ step_post_fwd_kernel(const __grid_constant__ FwdLaunch F, const __grid_constant_
   }
   __syncthreads();
   if (!s_last) return;
-  if (tid < L.P) {
-    const PostPair& pp = L.pair[tid];
+  // per pair: block partials summed by all 256 threads in a FIXED order (thread t takes blocks
+  // t, t + 256, ...; then a fixed shuffle / shared-memory tree): bit-reproducible loss
+  for (int p = 0; p < L.P; ++p) {
+    const PostPair& pp = L.pair[p];
+    const int b0 = p * L.blocks_per_pair;
     double l = 0.0, e = 0.0;
-    const int b0 = tid * L.blocks_per_pair;
-    for (int i = 0; i < L.blocks_per_pair; ++i) {  // fixed order: bit-reproducible loss
+    float r4[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+    for (int i = tid; i < L.blocks_per_pair; i += 256) {
       l += __ldcg(L.blk_part + 2 * (b0 + i));
       e += __ldcg(L.blk_part + 2 * (b0 + i) + 1);
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(L.blk_range) + (b0 + i));
+      r4[0] = fminf(r4[0], q.x); r4[1] = fmaxf(r4[1], q.y);
+      r4[2] = fminf(r4[2], q.z); r4[3] = fmaxf(r4[3], q.w);
     }
-    L.out2[2 * tid] = (float)(pp.coef * l);
-    L.out2[2 * tid + 1] = (float)(pp.coef * e / (double)(*pp.scale));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+      r4[0] = fminf(r4[0], __shfl_xor_sync(0xffffffffu, r4[0], o));
+      r4[1] = fmaxf(r4[1], __shfl_xor_sync(0xffffffffu, r4[1], o));
+      r4[2] = fminf(r4[2], __shfl_xor_sync(0xffffffffu, r4[2], o));
+      r4[3] = fmaxf(r4[3], __shfl_xor_sync(0xffffffffu, r4[3], o));
+    }
+    __syncthreads();  // (shared arrays are reused from pair to pair)
+    if (lane == 0) {
+      sh[0][w] = l;
+      sh[1][w] = e;
+      shr[0][w] = r4[0]; shr[1][w] = r4[1]; shr[2][w] = r4[2]; shr[3][w] = r4[3];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      l = e = 0.0;
+      for (int i = 0; i < 8; ++i) {
+        l += sh[0][i];
+        e += sh[1][i];
+        r4[0] = fminf(r4[0], shr[0][i]); r4[1] = fmaxf(r4[1], shr[1][i]);
+        r4[2] = fminf(r4[2], shr[2][i]); r4[3] = fmaxf(r4[3], shr[3][i]);
+      }
+      L.out2[2 * p] = (float)(pp.coef * l);
+      L.out2[2 * p + 1] = (float)(pp.coef * e / (double)(*pp.scale));
+      // (min, max) of this rank's log-sum-exps: the backward kernel decides from them (and from
+      // the other ranks') whether its one-exponential form is safe, instead of scanning the vectors
+      for (int k = 0; k < 4; ++k) pp.range[k] = r4[k];
+      shr[0][0] = r4[0]; shr[1][0] = r4[1]; shr[2][0] = r4[2]; shr[3][0] = r4[3];
+    }
+    __syncthreads();
+    if (pp.push_lse && tid < L.world) {
+      float* q = reinterpret_cast<float*>(L.peers[tid] + L.buf_off + pp.range_off) + 4 * L.rank;
+      for (int k = 0; k < 4; ++k) q[k] = shr[k][0];
+    }
   }
+  __syncthreads();  // the range pushes happen-before the flag release below
   if (tid == 0) {
     bool ok = L.local_ok != 0 && __ldcg(L.hdr + kHdrErr) == 0ull &&
               __ldcg(L.hdr + kHdrDup) != (unsigned long long)L.gen;

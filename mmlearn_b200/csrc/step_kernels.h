@@ -51,6 +51,8 @@ struct PostPair {
   const float* scale;
   int push_lse;
   unsigned long long lse_off[2];  // arena-buffer offsets of the gathered lse_a / lse_b
+  float* range;                   // [4] (min, max) of lse_a, (min, max) of lse_b of this rank
+  unsigned long long range_off;   // arena-buffer offset of range[world][4] (push_lse)
 };
 
 struct PostIds {
@@ -66,7 +68,8 @@ struct PostLaunch {
   int blocks_per_pair, main_blocks, total_blocks;
   unsigned gen;
   unsigned long long* hdr;
-  double* blk_part;
+  double* blk_part;   // [main blocks][2] loss / esum partial sums
+  float* blk_range;   // [main blocks][4] (min, max) of lse_a, lse_b
   float* out2;
   unsigned long long* ticket;
   unsigned long long ticket_target;

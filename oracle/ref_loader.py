@@ -211,3 +211,38 @@ def load_reference_retrieval() -> types.ModuleType:
     _CACHE["retrieval"] = _load("mmlearn.modules.metrics.retrieval_recall",
                                 "mmlearn/modules/metrics/retrieval_recall.py")
     return _CACHE["retrieval"]
+
+
+def load_reference_zero_shot() -> types.ModuleType:
+    """The unmodified ``mmlearn/tasks/zero_shot_classification.py`` under import stubs.
+
+    What the file imports but this image lacks is stubbed: ``lightning.pytorch`` (type names and
+    ``move_data_to_device``), the torchmetrics class names (``Accuracy`` ... -- never
+    instantiated by the fixture generator, which injects a capturing collection) and
+    ``CombinedDataset``.  ``evaluation_step`` -- the scoring arithmetic the fused path replaces --
+    is the reference's own code."""
+    if "zero_shot" in _CACHE:
+        return _CACHE["zero_shot"]
+    load_reference()
+
+    def mod(name):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+
+    lp = mod("lightning.pytorch")
+    lp.LightningModule = object
+    sys.modules["lightning"].pytorch = lp
+    lpu = mod("lightning.pytorch.utilities")
+    lpu.move_data_to_device = lambda data, device: data
+    lpr = mod("lightning.pytorch.utilities.rank_zero")
+    lpr.rank_zero_warn = lambda msg, *a, **k: warnings.warn(msg)
+    tm = sys.modules["torchmetrics"]
+    for name in ("AUROC", "Accuracy", "F1Score", "MetricCollection", "Precision", "Recall"):
+        setattr(tm, name, type(name, (), {}))
+    core = sys.modules["mmlearn.datasets.core"]
+    core.CombinedDataset = type("CombinedDataset", (), {})
+    _load("mmlearn.tasks.hooks", "mmlearn/tasks/hooks.py")
+    _CACHE["zero_shot"] = _load("mmlearn.tasks.zero_shot_classification",
+                                "mmlearn/tasks/zero_shot_classification.py")
+    return _CACHE["zero_shot"]

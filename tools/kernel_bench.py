@@ -76,3 +76,33 @@ for b in (32768, 4096, 16384):
                                               ptr(scale), ptr(src), 1, ptr(inv), 1, None, ptr(grad), 1, 1,
                                               st), "u"),
            f"unpack_grad      n={b} (bf16 out, direct)")
+
+# kernel durations without launch gaps (CUPTI), for the small shape where gaps matter
+if os.environ.get("MMCL_KB_PROFILE", "1") == "1":
+    from torch.profiler import ProfilerActivity, profile
+
+    b = 4096
+    x = torch.randn(b, d, device=dev, generator=g).to(torch.bfloat16)
+    xinv = (1 / x.float().norm(dim=1)).contiguous()
+    lse = torch.empty(b, device=dev)
+    es = torch.empty(b, device=dev)
+    wsb = lib.mmcl_sim_lse_workspace_bytes(h, b, N, d)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    lse_c = torch.full((N,), math.log(N) + 2.0, device=dev)
+    dx = torch.empty(b, d, device=dev)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            flush.fill_(1)
+            check(lib.mmcl_sim_lse_fwd(h, ptr(x), b, ptr(y), N, d, ptr(scale), ptr(xinv), ptr(yinv),
+                                       ptr(lse), ptr(es), ptr(ws), wsb, st), "f")
+            flush.fill_(1)
+            check(lib.mmcl_sim_grad_bwd_lse(h, ptr(x), b, ptr(y), N, d, ptr(scale), ptr(xinv), ptr(yinv),
+                                            ptr(lse), 2.0 * b, ptr(lse_c), 2.0 * b, ptr(dx), 1, st), "b")
+        torch.cuda.synchronize()
+    evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                 key=lambda e: e.time_range.start)
+    prev = evs[0].time_range.start
+    for e in evs:
+        print(f"  dur {e.time_range.end - e.time_range.start:8.1f}  gap {e.time_range.start - prev:7.1f}  {e.name[:60]}")
+        prev = e.time_range.end
