@@ -249,13 +249,19 @@ def main():
     pairs = [LossPairSpec((a_, b_), w_) for a_, b_, w_ in pair_cfg]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    host_split = {"fwd": [], "bwd": []}  # host seconds spent inside forward / backward calls
+
     def one_step(embs, ids, log_s):
         for t_ in embs.values():
             t_.grad = None
         log_s.grad = None
+        t0_ = time.perf_counter()
         loss = fn({f"{m}_embedding": embs[m] for m in mods}, {m: ids for m in mods},
                   log_s.exp(), pairs)
+        t1_ = time.perf_counter()
         loss.backward()
+        host_split["fwd"].append(t1_ - t0_)
+        host_split["bwd"].append(time.perf_counter() - t1_)
         return loss
 
     def barrier():
@@ -337,6 +343,8 @@ def main():
     read_ev = [None, None]
     e2e_losses = []
     host_t = []
+    host_split["fwd"].clear()
+    host_split["bwd"].clear()
     for i in range(total):
         if i + 1 < total:
             issue_copy(i + 1)
@@ -363,6 +371,8 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = N / (float(t2) / e2e_steps * 1e-3)
     host_dt = sorted((b_ - a_) * 1e3 for a_, b_ in zip(host_t[2:-1], host_t[3:]))
+    med = lambda v: sorted(v)[len(v) // 2] * 1e3 if v else None  # noqa: E731
+    host_fwd_ms, host_bwd_ms = med(host_split["fwd"][2:]), med(host_split["bwd"][2:])
     h2d = sum(h_emb[m].numel() * 2 for m in mods) + h_ids.numel() * 8 + 4 * max(P, 1)
     d2h = 4 * (1 + max(P, 1))
     e2e_ok = all(math.isfinite(v) and abs(v - loss_value) <= 1e-3 * abs(loss_value)
@@ -536,6 +546,8 @@ def main():
                     "d2h_bytes_per_step": d2h,
                     "host_ms_per_step": {"median": host_dt[len(host_dt) // 2] if host_dt else None,
                                          "max": host_dt[-1] if host_dt else None,
+                                         "in_forward_call": host_fwd_ms,
+                                         "in_backward_call": host_bwd_ms,
                                          "note": "rank 0's host loop period; a single long step "
                                                  "(allocator, page faults) shows up as max >> median"},
                     "how": "one event pair over all K steps incl. H2D copies, L2 flushes, kernels "

@@ -411,8 +411,13 @@ class _Run:
         parity = tr.parity if world > 1 else 0
         launch_grad = bool(self.need_grad and m.eager_backward)
         self.states = [sp]  # claims the arena buffer until backward() / release()
-        if not sp.forward(parity, local_ok, es, ids, self.scale, ws, launch_grad, _stream(dev)):
+        m._resolve_deferred()  # (a plan holds one verification at a time)
+        deferred = bool(m.deferred_verification)
+        if not sp.forward(parity, local_ok, es, ids, self.scale, ws, launch_grad, _stream(dev),
+                          verify=not deferred):
             return None
+        if deferred:
+            m._deferred = (self, sp)
         self.fast = (sp, parity, es, ws)
         m.steady_steps += 1
         self.grad_kernels_done = launch_grad
@@ -816,6 +821,10 @@ class _Run:
         gout = gout.detach().to(device=dev, dtype=torch.float32).contiguous()
         by_key = dict(zip((md.embedding for md in sp.mods),
                           sp.backward(parity, es, self.scale, ws, gout, st)))
+        if self.m._deferred is not None and self.m._deferred[0] is self:
+            # deferred verification: checked once the whole backward pass has been enqueued, i.e.
+            # before loss.backward() returns and long before an optimizer could use the gradients
+            torch.autograd.Variable._execution_engine.queue_callback(self.m._resolve_deferred)
         out = []
         for key in self.keys:
             src = self.embs[key]
@@ -943,6 +952,30 @@ class ContrastiveLoss(nn.Module):
         # under speculation, queue the gradient kernels at the end of forward (they need nothing
         # from backward()); set to False if the loss is often evaluated without back-propagation
         self.eager_backward = True
+        # Opt-in: do not wait for the device-side verification of a native step inside forward().
+        # forward() then returns without any host wait (the host can queue the encoders' backward
+        # straight away); the verification is checked at the end of loss.backward() -- or at the
+        # next forward() for a loss that is never back-propagated -- and a step whose batch did
+        # NOT have the assumed structure raises a RuntimeError there instead of being re-run
+        # transparently.  For training loops whose batch structure is fixed (drop_last, paired
+        # data); the default re-runs such a step through the general path.
+        self.deferred_verification = os.environ.get("MMCL_DEFER_VERIFY", "0") == "1"
+        self._deferred = None
+
+    def _resolve_deferred(self) -> None:
+        """Check the pending deferred verification, if any (see ``deferred_verification``)."""
+        pending, self._deferred = self._deferred, None
+        if pending is None:
+            return
+        run, sp = pending
+        if not sp.verify():
+            self._plan_cache.clear()
+            self._steady.clear()
+            raise RuntimeError(
+                "mmlearn_b200.ContrastiveLoss(deferred_verification=True): the previous step's "
+                "batch did not have the structure of the step before it (example ids not "
+                "identical row by row in every pair on every rank, or duplicated); its loss and "
+                "gradients are invalid. Re-run the step; it will take the general path.")
 
     def _remember_labels(self, plan: PairPlan, device) -> None:
         """contrastive.py:190-219: rebuild when the logit width changes or the device is new."""
@@ -963,6 +996,7 @@ class ContrastiveLoss(nn.Module):
         modality_loss_pairs: list[LossPairSpec],
     ) -> torch.Tensor:
         """Calculate the contrastive loss (same contract as contrastive.py:59-85)."""
+        self._resolve_deferred()
         if not embeddings:
             raise ValueError("embeddings is empty")
         keys = list(embeddings.keys())

@@ -103,8 +103,10 @@ class SteadyPlan:
         return True, es, ids
 
     def forward(self, parity: int, local_ok: bool, es: list, ids: list, scale: torch.Tensor,
-                ws: torch.Tensor, launch_grad: bool, stream: int) -> bool:
-        """Enqueue the step and verify the assumption; False = mis-speculation."""
+                ws: torch.Tensor, launch_grad: bool, stream: int, verify: bool = True) -> bool:
+        """Enqueue the step and verify the assumption; False = mis-speculation.
+        ``verify=False`` returns at once (True); the caller must call :meth:`verify` before it
+        trusts the step's results and before the next ``forward`` of this plan."""
         lib = _lib.load()
         if local_ok:
             e_arr = (c_void_p * self.M)(*[t.data_ptr() for t in es])
@@ -114,8 +116,12 @@ class SteadyPlan:
         check(lib.mmcl_step_forward(self.step, parity, int(local_ok), e_arr, i_arr,
                                     scale.data_ptr(), ws.data_ptr(), int(launch_grad), stream),
               "mmcl_step_forward")
+        return self.verify() if verify else True
+
+    def verify(self) -> bool:
+        """Wait for the verification word of the last forward (not for the stream)."""
         ok = c_int(0)
-        check(lib.mmcl_step_verify(self.step, ctypes.byref(ok)), "mmcl_step_verify")
+        check(_lib.load().mmcl_step_verify(self.step, ctypes.byref(ok)), "mmcl_step_verify")
         return bool(ok.value)
 
     def grad_kernels(self, parity: int, scale: torch.Tensor, ws: torch.Tensor, stream: int):

@@ -80,7 +80,12 @@ class ContrastiveLossHead(nn.Module):
             self.register_buffer("log_logit_scale", log_s)
 
     def logit_scale(self) -> torch.Tensor:
-        """Clamp the parameter in place and return exp of it (one kernel)."""
+        """Training: clamp the parameter in place and return exp of it (one kernel), as
+        ``training_step`` does (contrastive_pretraining.py:488-489).  Evaluation: the reference
+        only exponentiates (``_shared_eval_step`` -> ``_compute_loss``, :607-611) -- the parameter
+        is left untouched."""
+        if not self.training:
+            return self.log_logit_scale.exp()
         return _ClampExp.apply(self.log_logit_scale, self.max_logit_scale)
 
     def forward(self, outputs: dict, example_ids: dict) -> torch.Tensor:

@@ -152,3 +152,42 @@ def test_two_forwards_before_backward():
             assert float(b[key].grad.float().cpu().norm()) == pytest.approx(2 * float(r.norm()), rel=1e-2)
         assert float(s.grad) == pytest.approx(3 * ref.dscale[0], rel=1e-2,
                                               abs=6e-3 * ref.dscale_gross[0])
+
+
+def test_deferred_verification():
+    """Opt-in ``deferred_verification``: forward() does not wait for the device; a valid step gives
+    the reference's numbers, a step whose ids lost the assumed structure raises at the end of
+    backward (before any optimizer could run) and the following call takes the general path."""
+    from mmlearn_b200 import ContrastiveLoss
+
+    n, d = 512, 128
+    emb, ids = synthetic_inputs(n, d)
+    flags = dict(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    ref = contrastive_oracle(emb, ids, 1 / 0.07, [OPair(("rgb", "text"))], fast_match=True, **flags)
+    fn = ContrastiveLoss(**flags)
+    fn.deferred_verification = True
+    pairs = [("rgb", "text", 1.0)]
+    for k in range(3):
+        loss, leaves, s = _step(fn, emb[0], ids[0], 1 / 0.07, pairs, torch.bfloat16)
+        _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
+    assert fn.steady_steps == 2
+    ids2 = {k: v.copy() for k, v in ids[0].items()}
+    ids2["text"] = ids2["text"][np.random.RandomState(3).permutation(n)]
+    with pytest.raises(RuntimeError, match="deferred_verification"):
+        _step(fn, emb[0], ids2, 1 / 0.07, pairs, torch.bfloat16)
+    ref2 = contrastive_oracle([emb[0]], [ids2], 1 / 0.07, [OPair(("rgb", "text"))], **flags)
+    loss, leaves, s = _step(fn, emb[0], ids2, 1 / 0.07, pairs, torch.bfloat16)  # general path
+    _compare(loss, leaves, s, ref2.losses[0], ref2.grads[0], ref2.dscale[0], ref2.dscale_gross[0])
+    # forward-only calls are checked at the next call
+    e = {k: v.to(DEV).to(torch.bfloat16) for k, v in emb[0].items()}
+    good = {k: torch.from_numpy(v).to(DEV) for k, v in ids[0].items()}
+    bad = {k: torch.from_numpy(v).to(DEV) for k, v in ids2.items()}
+    from mmlearn_b200 import LossPairSpec
+
+    sc = torch.tensor(1 / 0.07, device=DEV)
+    with torch.no_grad():
+        fn(e, good, sc, [LossPairSpec(("rgb", "text"))])
+        fn(e, good, sc, [LossPairSpec(("rgb", "text"))])
+        fn(e, bad, sc, [LossPairSpec(("rgb", "text"))])  # native step on a batch that does not fit
+        with pytest.raises(RuntimeError, match="deferred_verification"):
+            fn(e, good, sc, [LossPairSpec(("rgb", "text"))])

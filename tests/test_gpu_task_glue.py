@@ -63,3 +63,21 @@ def test_head_buffer_scale_and_default_pairs():
     ref = contrastive_oracle(emb, ids, 10.0, pairs, l2_normalize=True, local_loss=True,
                              gather_with_grad=True, fast_match=True)
     assert float(loss) == pytest.approx(ref.losses[0], rel=1e-3)
+
+
+def test_eval_mode_does_not_clamp_the_parameter():
+    """The reference clamps ``log_logit_scale`` only in ``training_step``
+    (contrastive_pretraining.py:488-489); evaluation just exponentiates it."""
+    import math
+
+    from mmlearn_b200.task import ContrastiveLossHead
+
+    head = ContrastiveLossHead().to("cuda:0")
+    with torch.no_grad():
+        head.log_logit_scale.fill_(math.log(250.0))  # above max_logit_scale = 100
+    head.eval()
+    assert float(head.logit_scale()) == pytest.approx(250.0, rel=1e-5)
+    assert float(head.log_logit_scale) == pytest.approx(math.log(250.0), rel=1e-6)
+    head.train()
+    assert float(head.logit_scale()) == pytest.approx(100.0, rel=1e-5)
+    assert float(head.log_logit_scale) == pytest.approx(math.log(100.0), rel=1e-6)
