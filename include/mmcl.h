@@ -193,6 +193,34 @@ int mmcl_sim_logits_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const vo
                         int64_t nk, int64_t d, double scale, const float* qinv, const float* kinv,
                         float* out, int64_t out_ld, mmcl_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Modality-alignment term on the same mainloops.
+ * The reference builds an all-vs-all [T, T] logit matrix over the concatenated embeddings of all
+ * modalities, a dense 0/1 target (diagonal + an upper-triangular block per modality, built from
+ * an O(T^2) Python list) and applies binary cross-entropy with logits.  Here the targets are a
+ * per-row column band [i, band_hi[i]) evaluated from tile coordinates, and nothing [T, T] exists:
+ *   mmcl_sim_bce_fwd: for query rows i = row_base .. row_base + nq - 1 of the keys,
+ *                     x_ij = s * qinv_i * kinv_j * (q_i . k_j):
+ *       stats[0*nq + r] = sum_j softplus(x_ij)          stats[3*nq + r] = sum_j sigmoid(x_ij) x_ij
+ *       stats[1*nq + r] = sum_{j in band} softplus(x_ij) stats[4*nq + r] = sum_{j in band} sigmoid x
+ *       stats[2*nq + r] = sum_{j in band} x_ij
+ *     (loss_pos = [1] - [2], loss_neg = [0] - [1]; d loss / d s from [2..4])
+ *   mmcl_sim_bce_bwd: dx[r,:] += sum_j G_rj * yinv_j * y[j,:] with
+ *       G_ij = sigmoid(x_ij) (a_ij + a_ji) - (t_ij p_i + t_ji p_j),  t_ij = [j in band_i],
+ *       a_ij = t_ij ? p_i : n_i,  p_i = 1/(T |band_i|),  n_i = 1/(T (T - |band_i|)),  T = ny
+ *     i.e. the gradient of the term with respect to the normalised row (before the factor s);
+ *     dx must be zero-filled by the caller; d must fit the CTA-pair kernel (multiple of 128).
+ * Replaces: _compute_modality_alignment_loss (contrastive.py:344-413) and its autograd backward.
+ * ------------------------------------------------------------------------------------------ */
+size_t mmcl_sim_bce_workspace_bytes(mmcl_handle* h, int64_t nq, int64_t nk, int64_t d);
+int mmcl_sim_bce_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16, int64_t nk,
+                     int64_t d, const float* scale, const float* qinv, const float* kinv,
+                     int64_t row_base, const int32_t* band_hi, float* stats, void* workspace,
+                     size_t workspace_bytes, mmcl_stream stream);
+int mmcl_sim_bce_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16, int64_t ny,
+                     int64_t d, const float* scale, const float* xinv, const float* yinv,
+                     int64_t row_base, const int32_t* band_hi, float* dx, mmcl_stream stream);
+
 /* Caller glue of the task: log_scale[i] <- clamp(log_scale[i], 0,
  * log(max_scale)) IN PLACE and scale_out[i] = exp(log_scale[i]), one launch.
  * Replaces: `self.log_logit_scale.clamp_(0, math.log(self.max_logit_scale))` followed by

@@ -60,6 +60,12 @@ SYMBOLS = {
     "mmcl_pack_rows_symm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                                     c_int64, c_int, c_size_t, c_int64, c_void_p]),
     "mmcl_symm_fence": (c_int, [c_void_p, c_void_p]),
+    "mmcl_sim_bce_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64, c_int64]),
+    "mmcl_sim_bce_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
+    "mmcl_sim_bce_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mmcl_sim_logits_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                     c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mmcl_debug_push": (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p]),

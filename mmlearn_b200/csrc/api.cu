@@ -445,6 +445,55 @@ int mmcl_sim_logits_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const vo
   return MMCL_OK;
 }
 
+size_t mmcl_sim_bce_workspace_bytes(mmcl_handle* h, int64_t nq, int64_t nk, int64_t d) {
+  if (!h || nq <= 0 || nk <= 0 || d <= 0) return 0;
+  return sim_bce_workspace_bytes(h->num_sms, nq, nk, d);
+}
+
+int mmcl_sim_bce_fwd(mmcl_handle* h, const void* q_bf16, int64_t nq, const void* k_bf16, int64_t nk,
+                     int64_t d, const float* scale, const float* qinv, const float* kinv,
+                     int64_t row_base, const int32_t* band_hi, float* stats, void* workspace,
+                     size_t workspace_bytes, mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_sim_bce_fwd: null handle/scale");
+  int rc = check_sim_args("mmcl_sim_bce_fwd", q_bf16, nq, k_bf16, nk, d);
+  if (rc) return rc;
+  if (nq == 0) return MMCL_OK;
+  REQUIRE(nk > 0 && band_hi && stats, "mmcl_sim_bce_fwd: null band_hi / stats or no keys");
+  REQUIRE(row_base >= 0 && row_base + nq <= nk, "mmcl_sim_bce_fwd: query rows must be key rows");
+  if (workspace_bytes < sim_bce_workspace_bytes(h->num_sms, nq, nk, d) || !workspace)
+    return fail(MMCL_ERR_WORKSPACE, "mmcl_sim_bce_fwd: workspace too small");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const char* err = nullptr;
+  cudaError_t e = launch_sim_bce_fwd(h->num_sms, q_bf16, nq, k_bf16, nk, d, scale, qinv, kinv,
+                                     row_base, band_hi, stats, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream), &err);
+  if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_bce_fwd");
+  return MMCL_OK;
+}
+
+int mmcl_sim_bce_bwd(mmcl_handle* h, const void* x_bf16, int64_t nx, const void* y_bf16, int64_t ny,
+                     int64_t d, const float* scale, const float* xinv, const float* yinv,
+                     int64_t row_base, const int32_t* band_hi, float* dx, mmcl_stream stream) {
+  REQUIRE(h && scale, "mmcl_sim_bce_bwd: null handle/scale");
+  int rc = check_sim_args("mmcl_sim_bce_bwd", x_bf16, nx, y_bf16, ny, d);
+  if (rc) return rc;
+  if (nx == 0 || ny == 0) return MMCL_OK;
+  REQUIRE(band_hi && dx && (reinterpret_cast<uintptr_t>(dx) & 15) == 0,
+          "mmcl_sim_bce_bwd: null band_hi / dx (16-byte aligned)");
+  REQUIRE(row_base >= 0 && row_base + nx <= ny, "mmcl_sim_bce_bwd: x rows must be y rows");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const char* err = nullptr;
+  cudaError_t e = launch_sim_bce_bwd_pair(h->num_sms, x_bf16, nx, y_bf16, ny, d, scale, xinv, yinv,
+                                          row_base, band_hi, dx, static_cast<cudaStream_t>(stream),
+                                          &err);
+  if (e == cudaErrorNotSupported)
+    return fail(MMCL_ERR_INVALID, "mmcl_sim_bce_bwd: d must be a multiple of 128 (256 above 512)");
+  if (e != cudaSuccess) return err ? fail(MMCL_ERR_CUDA, err) : cuda_fail(e, "mmcl_sim_bce_bwd");
+  return MMCL_OK;
+}
+
 int mmcl_pair_loss(mmcl_handle* h, const float* lse_a, const float* lse_b, const float* esum_a,
                    const float* esum_b, const float* pos, int64_t n, double weight, double n_norm,
                    const float* scale, float* out2, mmcl_stream stream) {

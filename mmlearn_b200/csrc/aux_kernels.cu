@@ -71,6 +71,7 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, long long src_row
 #pragma unroll
       for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
     }
+    __syncwarp();  // (lanes leave the loop after different trip counts)
     ss = warp_sum(ss);
     inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
   }
@@ -118,6 +119,7 @@ __global__ void positive_logits_kernel(const __nv_bfloat16* __restrict__ q, long
       for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
     }
   }
+  __syncwarp();
   acc = warp_sum(acc);
   if (lane == 0) {
     float f = scale ? *scale : 1.f;
@@ -235,24 +237,28 @@ __global__ void unpack_grad_kernel(const float* __restrict__ dacc,
   float dot = 0.f;
   const float inv = normalize ? inv_norm[row] : 1.f;
   const float pc = pos_coef * (partner_inv ? partner_inv[row] : 1.f);
+  // Every lane walks every column group with a clamped address and a 0/1 mask instead of
+  // branching on `c < d`: the warp stays converged up to the shuffle reduction below (a divergent
+  // `if` in front of it gave lane-dependent sums for d % 256 not in {0, 64, 128}).
 #pragma unroll
   for (int nv = 0; nv < MAXV; ++nv) {
     const int c = lane * 8 + nv * 256;
-    if (c < d) {
-      float pa[8];
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(dacc + row * d + c));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(dacc + row * d + c + 4));
-      load8<1>(partner, row * d + c, pa);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const bool act = c < d;
+    const int cc = act ? c : 0;
+    float pa[8];
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(dacc + row * d + cc));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(dacc + row * d + cc + 4));
+    load8<1>(partner, row * d + cc, pa);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pc * pa[i]);
-      if (normalize) {
-        load8<DT>(src, srow * d + c, x[nv]);
+    for (int i = 0; i < 8; ++i) g[nv][i] = act ? coef * (a[i] - pc * pa[i]) : 0.f;
+    if (normalize) {
+      load8<DT>(src, srow * d + cc, x[nv]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[nv][i] * inv, dot);
-      }
+      for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[nv][i] * inv, dot);
     }
   }
+  __syncwarp();
   if (normalize) dot = warp_sum(dot);
   const bool clamped = inv >= 0.99e12f;  // ||x|| < eps: x_hat = x / eps, a plain scaling
 #pragma unroll

@@ -48,6 +48,8 @@ struct FwdSub {  // one direction of one pair, restricted to a rotated range of 
   float* out;                 // store mode: [nq, out_ld] fp32 logits
   long long out_ld;
   float out_scale;
+  long long row_base;         // BCE mode: key index of query row 0
+  const int* band_hi;         // BCE mode: [nk] end of every key row's positive band
 };
 
 constexpr int kMaxPushSegs = 16;
@@ -122,6 +124,12 @@ struct BwdProb {  // one side of one pair: dX = sum_j G_ij yinv_j Y_j
   const float* rng_row;  // [2]
   const float* rng_col;  // [rng_col_count][rng_col_stride floats], (min, max) first
   int rng_col_stride, rng_col_count;
+  // binary-cross-entropy form of G (modality-alignment term, contrastive.py:344-413):
+  //   G_ij = sigmoid(x_ij) (a_ij + a_ji) - (t_ij p_i + t_ji p_j),  t_ij = j in [i, band_hi[i]),
+  //   a_ij = t_ij ? p_i : n_i,  p_i = 1 / (T |band_i|),  n_i = 1 / (T (T - |band_i|))
+  int bce;
+  long long row_base;    // index of x row 0 among the y rows
+  const int* band_hi;    // [ny]
 };
 
 struct BwdLaunch {

@@ -32,6 +32,13 @@ cudaError_t launch_sim_logits_fwd(int num_sms, const void* q, long long nq, cons
                                   const float* kinv, float* out, long long out_ld,
                                   cudaStream_t stream, const char** err);
 
+size_t sim_bce_workspace_bytes(int num_sms, long long nq, long long nk, long long d);
+cudaError_t launch_sim_bce_fwd(int num_sms, const void* q, long long nq, const void* k,
+                               long long nk, long long d, const float* scale, const float* qinv,
+                               const float* kinv, long long row_base, const int* band_hi,
+                               float* stats, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream, const char** err);
+
 // sim_fwd.cu, fused launches: fwd_begin, fwd_add_sub per (pair, direction[, key range]),
 // fwd_finish (CTA split + partial-statistics sizes), then fill the pointers and launch
 void fwd_begin(FwdLaunch* L, long long d);
@@ -49,6 +56,12 @@ size_t bwd_finish(BwdLaunch* L, int num_sms);
 int bwd_cta_pairs(const BwdLaunch& L);
 int bwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d);
 cudaError_t launch_bwd_fused(const TensorMaps& maps, const BwdLaunch& L, cudaStream_t stream);
+
+cudaError_t launch_sim_bce_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
+                                    long long ny, long long d, const float* scale,
+                                    const float* xinv, const float* yinv, long long row_base,
+                                    const int* band_hi, float* dx, cudaStream_t stream,
+                                    const char** err);
 
 // sim_bwd.cu
 cudaError_t launch_sim_grad_bwd(int num_sms, const void* x, long long nx, const void* y,

@@ -133,6 +133,38 @@ __device__ __forceinline__ void conv16_fast(const uint32_t (&v)[16], uint32_t* g
   }
 }
 
+// BCE form (BwdProb::bce).  cy[e] = (band end of column j as int bits, 1/||y_j||); `jg0` = global
+// index of the first of the 16 columns.  Three MUFU per logit (ex2, rcp for the sigmoid, rcp for
+// the column coefficient); the alignment term is not the headline path.
+__device__ __forceinline__ void conv16_bce(const uint32_t (&v)[16], uint32_t* g, float crow,
+                                           long long ig, long long bh_i, float p_i, float n_i,
+                                           float tt, long long jg0, long long ny,
+                                           const float2* cy) {
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float gg[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 f = cy[e + h];
+      const long long jg = jg0 + e + h;
+      const long long bh_j = (long long)__float_as_int(f.x);
+      const float x = __uint_as_float(v[e + h]) * f.y * crow;
+      const float u = ex2f(-fabsf(x) * LOG2E);
+      const float r = __frcp_rn(1.f + u);
+      const float sig = x >= 0.f ? r : u * r;
+      const bool t_ij = jg >= ig && jg < bh_i;
+      const bool t_ji = ig >= jg && ig < bh_j;
+      const float np_j = float(bh_j - jg);                       // |band_j|
+      const float a_ji = __frcp_rn(tt * (t_ji ? np_j : tt - np_j));
+      const float a_ij = t_ij ? p_i : n_i;
+      float gv = sig * (a_ij + a_ji) - ((t_ij ? p_i : 0.f) + (t_ji ? a_ji : 0.f));
+      if (jg >= ny) gv = 0.f;
+      gg[h] = gv * f.y;
+    }
+    g[e >> 1] = pack_bf16x2(gg[0], gg[1]);
+  }
+}
+
 constexpr int NTHREADS = 384;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
@@ -443,7 +475,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
       const int grow = xt * BM + row;
       if (t == t_begin) seg_head = yt != 0;
-      const int mode = (p.off_row ? 1 : 0) | (p.off_col ? 2 : 0);
+      const int mode = p.bce ? 4 : ((p.off_row ? 1 : 0) | (p.off_col ? 2 : 0));
       const bool fast = s_fast[pi] != 0;
       const float mu = s_mu[pi];
       if (own) {
@@ -452,6 +484,17 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
                                ? fmaf(__ldcg(p.off_row + grow), p.off_mul, p.row_add) : INFINITY;
         const float cc = c0 * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
         const float R = (fast && grow < p.nx) ? ex2f(offr - mu) : 0.f;
+        // BCE form: this row's band and coefficients
+        const float tt = float(p.ny);
+        const long long ig = p.row_base + grow;
+        long long bh_i = ig + 1;
+        if (mode == 4 && grow < p.nx) {
+          const long long b0 = (long long)p.band_hi[ig];
+          if (b0 > bh_i) bh_i = b0;
+        }
+        const float crow = (*p.scale) * ((p.xinv && grow < p.nx) ? p.xinv[grow] : 1.f);
+        const float p_i = __frcp_rn(tt * float(bh_i - ig));
+        const float n_i = __frcp_rn(tt * (tt - float(bh_i - ig)));
         named_bar_sync(1, 256);  // everyone is done with the previous step's column data
         {
           const int j = wg * 128 + et;
@@ -460,6 +503,14 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           v2.x = (p.off_col && gy < p.ny) ? fmaf(__ldcg(p.off_col + gy), p.off_mul, p.col_add)
                                           : INFINITY;
           v2.y = (p.yinv && gy < p.ny) ? p.yinv[gy] : 1.f;
+          if (mode == 4) {
+            int bh = gy + 1;
+            if (gy < p.ny) {
+              const int b0 = p.band_hi[gy];
+              if (b0 > bh) bh = b0;
+            }
+            v2.x = __int_as_float(bh);
+          }
           if (fast) {
             // pair-planar layout for the packed-math path: (cyB0, cyB1, yinv0, yinv1)
             float* f = reinterpret_cast<float*>(sCol) + (j >> 1) * 4 + (j & 1);
@@ -485,7 +536,10 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         uint32_t va[16], vb[16], g[16];
         const uint32_t sbase = tm_s + lane_base;
         auto convert = [&](const uint32_t (&v)[16], uint32_t* gout, int col) {
-          if (fast)
+          if (mode == 4)
+            conv16_bce(v, gout, crow, ig, bh_i, p_i, n_i, tt, (long long)yt * BNY + col, p.ny,
+                       sCol + col);
+          else if (fast)
             conv16_fast(v, gout, cc, offr, R, reinterpret_cast<const float4*>(sCol) + (col >> 1));
           else if (mode == 3)
             conv16<3>(v, gout, cc, offr, sCol + col);
@@ -658,6 +712,38 @@ cudaError_t launch_bwd_fused(const TensorMaps& maps, const BwdLaunch& L, cudaStr
   sim_grad_bwd_pair_kernel<<<2 * bwd_cta_pairs(L), NTHREADS, smem, stream>>>(maps, L);
   count_launches(1);
   return cudaGetLastError();
+}
+
+// BCE form of the recompute backward (one problem, accumulating into a zero-filled dx).
+cudaError_t launch_sim_bce_bwd_pair(int num_sms, const void* x, long long nx, const void* y,
+                                    long long ny, long long d, const float* scale,
+                                    const float* xinv, const float* yinv, long long row_base,
+                                    const int* band_hi, float* dx, cudaStream_t stream,
+                                    const char** err) {
+  if (!bwd_pair_supported(num_sms, d)) return cudaErrorNotSupported;
+  BwdLaunch L;
+  bwd_begin(&L, d);
+  bwd_add_prob(&L, nx, ny);
+  bwd_finish(&L, num_sms);
+  BwdProb& p = L.prob[0];
+  p.scale = scale;
+  p.xinv = xinv;
+  p.yinv = yinv;
+  p.bce = 1;
+  p.row_base = row_base;
+  p.band_hi = band_hi;
+  p.dx = dx;
+  TensorMaps maps;
+  if (make_tmap_bf16_sw128(&maps.tm[0], x, nx, d, d, BM) ||
+      make_tmap_bf16_sw128(&maps.tm[1], y, ny, d, d, BNY) ||
+      make_tmap_bf16_sw128(&maps.tm[2], y, ny, d, d, 64)) {
+    *err = "sim_bce_bwd: cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  p.map_x = 0;
+  p.map_y256 = 1;
+  p.map_y64 = 2;
+  return launch_bwd_fused(maps, L, stream);
 }
 
 // Returns cudaErrorNotSupported (without launching) when the shape does not fit the pair form;

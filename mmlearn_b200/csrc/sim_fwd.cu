@@ -77,6 +77,11 @@ __device__ __forceinline__ int find_sub(const FwdLaunch& L, long long t, int s) 
   return s;
 }
 
+// kMode == 3: binary-cross-entropy row statistics of the modality-alignment term
+// (contrastive.py:344-413): the all-vs-all logits x_ij = s * cos_ij with targets t_ij = 1 on the
+// band j in [i, band_hi[i]) of row i (diagonal + the reference's upper-triangular same-modality
+// blocks, built from tile coordinates).  Per row: sum softplus(x), and over the band: sum
+// softplus(x), sum x; plus sum sigmoid(x) x over all columns and over the band (d loss / d scale).
 // kMode == 0: online log-sum-exp epilogue (the loss).  kMode == 2: the logits themselves are
 // stored, out[i, j] = out_scale * qinv_i * kinv_j * (q_i . k_j) (zero-shot classification scores:
 // few keys, every score needed by the metric collection).  kMode == 1: the same mainloop with a
@@ -326,7 +331,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
       const float* kinv = S.kinv;
       const int nk = S.nk;
       constexpr bool kRank = kMode == 1;
-      const float s = kMode == 0 ? *S.scale : 1.f;
+      const float s = kMode == 0 ? *S.scale : 1.f;  // (modes 1-3 read what they need themselves)
       const bool neg = s < 0.f;
       float m = -INFINITY, l = 0.f, tt = 0.f;
       const int grow = qt * BM + row;
@@ -355,6 +360,69 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         return __ldcg(kinv + gk);
       };
       float knext = key_factor(tile_of(j0));  // prefetched one tile ahead
+      if (kMode == 3) {
+        const float crow = (*S.scale) * ((S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f);
+        const long long ig = S.row_base + grow;  // this row's index among the keys
+        long long bh = (grow < S.nq) ? (long long)S.band_hi[ig] : 0;
+        if (bh < ig + 1) bh = ig + 1;  // the diagonal is always a positive
+        float sA = 0.f, sB = 0.f, sC = 0.f, sE = 0.f, sF = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          const int kt = tile_of(j);
+          const uint32_t ab = acc & 1, aphase = (acc >> 1) & 1;
+          float* kv = sKinv + ab * BN;
+          kv[et] = knext;
+          if (j + 1 < j1) knext = key_factor(tile_of(j + 1));
+          named_bar_sync(1, 256);
+          mbar_wait(&acc_full[ab], aphase);
+          tc_fence_after();
+          const uint32_t taddr = tmem + ab * BN + (uint32_t(q * 32) << 16);
+          const int valid = nk - kt * BN;
+#pragma unroll 1
+          for (int ch = ch0; ch < ch0 + BN / 64; ++ch) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            if (ch == ch0 + BN / 64 - 1) {
+              tc_fence_before();
+              mbar_arrive(&acc_empty[ab]);
+            }
+            const int cv = valid - ch * 32;
+            const float* kc = kv + ch * 32;
+            const long long c0 = (long long)kt * BN + ch * 32;  // first column of this chunk
+            float a = 0.f, b = 0.f, c = 0.f, e2 = 0.f, f2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = __uint_as_float(v[e]) * kc[e] * crow;
+              const float u = ex2f(-fabsf(x) * LOG2E);        // exp(-|x|)
+              const float sp = fmaxf(x, 0.f) + lg2f(1.f + u) * LN2;  // softplus(x)
+              const float r = __frcp_rn(1.f + u);
+              const float sx = (x >= 0.f ? r : u * r) * x;     // sigmoid(x) * x
+              const bool ok = e < cv;
+              const bool pos = ok && (c0 + e >= ig) && (c0 + e < bh);
+              a += ok ? sp : 0.f;
+              e2 += ok ? sx : 0.f;
+              b += pos ? sp : 0.f;
+              c += pos ? x : 0.f;
+              f2 += pos ? sx : 0.f;
+            }
+            sA += a; sB += b; sC += c; sE += e2; sF += f2;
+          }
+          ++acc;
+        }
+        const long long first_tile = S.tile_begin - S.phase_begin + (long long)qt * S.nkt_sub;
+        const int c_first = int(first_tile / S.tpc);
+        const int slot = 2 * (int(blockIdx.x) - c_first) + wg;
+        const long long stride = (long long)S.nqt * BM;
+        const long long o = (long long)slot * stride + (long long)qt * BM + row;
+        const long long plane = (long long)S.max_slots * stride;
+        S.part[o] = sA;
+        S.part[plane + o] = sB;
+        S.part[2 * plane + o] = sC;
+        S.part[3 * plane + o] = sE;
+        S.part[4 * plane + o] = sF;
+        t += j1 - j0;
+        continue;
+      }
       if (kMode == 2) {
         const float cq = S.out_scale * ((S.qinv && grow < S.nq) ? S.qinv[grow] : 1.f);
         for (int j = j0; j < j1; ++j) {
@@ -785,6 +853,54 @@ cudaError_t launch_sim_rank_fwd(int num_sms, const void* q, long long nq, const 
   e = launch_fwd<1>(maps, L, stream);
   if (e != cudaSuccess) return e;
   rank_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], rank);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
+namespace {
+
+// Sum of the per-CTA partial BCE statistics of each row: stats[k * nq + row], k = 0..4.
+__global__ void bce_combine_kernel(FwdSub S, float* __restrict__ stats) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= S.nq) return;
+  const int qt = row / BM;
+  const long long first_tile = S.tile_begin - S.phase_begin + (long long)qt * S.nkt_sub;
+  const int c_first = int(first_tile / S.tpc);
+  const int c_last = int((first_tile + S.nkt_sub - 1) / S.tpc);
+  const long long stride = (long long)S.nqt * BM;
+  const long long plane = (long long)S.max_slots * stride;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int sl = 0; sl < 2 * (c_last - c_first + 1); ++sl)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] += S.part[k * plane + (long long)sl * stride + row];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) stats[(long long)k * S.nq + row] = acc[k];
+}
+
+}  // namespace
+
+size_t sim_bce_workspace_bytes(int num_sms, long long nq, long long nk, long long d) {
+  return sim_lse_workspace_bytes(num_sms, nq, nk, d) / 3 * 5;  // five statistics instead of three
+}
+
+cudaError_t launch_sim_bce_fwd(int num_sms, const void* q, long long nq, const void* k,
+                               long long nk, long long d, const float* scale, const float* qinv,
+                               const float* kinv, long long row_base, const int* band_hi,
+                               float* stats, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream, const char** err) {
+  FwdLaunch L;
+  TensorMaps maps;
+  cudaError_t e = single_problem(num_sms, q, nq, k, nk, d, workspace, workspace_bytes / 5 * 3, &L,
+                                 &maps, err, "sim_bce_fwd: workspace too small");
+  if (e != cudaSuccess) return e;
+  L.sub[0].scale = scale;
+  L.sub[0].qinv = qinv;
+  L.sub[0].kinv = kinv;
+  L.sub[0].row_base = row_base;
+  L.sub[0].band_hi = band_hi;
+  e = launch_fwd<3>(maps, L, stream);
+  if (e != cudaSuccess) return e;
+  bce_combine_kernel<<<(L.sub[0].nq + 255) / 256, 256, 0, stream>>>(L.sub[0], stats);
   count_launches(1);
   return cudaGetLastError();
 }

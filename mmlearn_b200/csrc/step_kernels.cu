@@ -456,37 +456,39 @@ __global__ void step_unpack_kernel(const __grid_constant__ UnpackLaunch L) {
   const float inv = L.normalize ? P.inv_norm[row] : 1.f;
   const float pc = P.pos_coef * (P.partner_inv ? P.partner_inv[row] : 1.f);
   const int xt = int(row >> 7), rin = int(row & 127);
+  // (converged walk with a clamped address and a 0/1 mask: see aux_kernels.cu unpack_grad_kernel)
 #pragma unroll
   for (int nv = 0; nv < MAXV; ++nv) {
     const int c = lane * 8 + nv * 256;
-    if (c < d) {
-      float pa[8];
-      float4 a0 = __ldcg(reinterpret_cast<const float4*>(P.dacc + row * d + c));
-      float4 a1 = __ldcg(reinterpret_cast<const float4*>(P.dacc + row * d + c + 4));
-      if (L.scratch) {
-        // segments of this (x tile, d pass) item that other CTA pairs continued
-        const int dc = c / L.dp, cin = c - dc * L.dp;
-        const long long t0 = P.tile_begin + ((long long)xt * L.ndc + dc) * P.nyt;
-        const long long c_first = t0 / L.per_pair, c_last = (t0 + P.nyt - 1) / L.per_pair;
-        for (long long cp = c_first + 1; cp <= c_last; ++cp) {
-          const float* sp = L.scratch + ((cp * 128 + rin) * (long long)L.dp + cin);
-          const float4 b0 = __ldcg(reinterpret_cast<const float4*>(sp));
-          const float4 b1 = __ldcg(reinterpret_cast<const float4*>(sp + 4));
-          a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
-          a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
-        }
-      }
-      load8(1, P.partner, row * d + c, pa);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[nv][i] = coef * (a[i] - pc * pa[i]);
-      if (L.normalize) {
-        load8(P.src_dtype, P.src, row * d + c, x[nv]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[nv][i] * inv, dot);
+    const bool act = c < d;
+    const int cc = act ? c : 0;
+    float pa[8];
+    float4 a0 = __ldcg(reinterpret_cast<const float4*>(P.dacc + row * d + cc));
+    float4 a1 = __ldcg(reinterpret_cast<const float4*>(P.dacc + row * d + cc + 4));
+    if (L.scratch) {
+      // segments of this (x tile, d pass) item that other CTA pairs continued
+      const int dc = cc / L.dp, cin = cc - dc * L.dp;
+      const long long t0 = P.tile_begin + ((long long)xt * L.ndc + dc) * P.nyt;
+      const long long c_first = t0 / L.per_pair, c_last = (t0 + P.nyt - 1) / L.per_pair;
+      for (long long cp = c_first + 1; cp <= c_last; ++cp) {
+        const float* sp = L.scratch + ((cp * 128 + rin) * (long long)L.dp + cin);
+        const float4 b0 = __ldcg(reinterpret_cast<const float4*>(sp));
+        const float4 b1 = __ldcg(reinterpret_cast<const float4*>(sp + 4));
+        a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+        a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
       }
     }
+    load8(1, P.partner, row * d + cc, pa);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[nv][i] = act ? coef * (a[i] - pc * pa[i]) : 0.f;
+    if (L.normalize) {
+      load8(P.src_dtype, P.src, row * d + cc, x[nv]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(g[nv][i], x[nv][i] * inv, dot);
+    }
   }
+  __syncwarp();
   if (L.normalize) dot = warp_sum(dot);
   const bool clamped = inv >= 0.99e12f;  // ||x|| < eps: x_hat = x / eps, a plain scaling
 #pragma unroll

@@ -126,6 +126,7 @@ __global__ void pack_rows_symm_kernel(const void* __restrict__ src, long long sr
 #pragma unroll
       for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
     }
+    __syncwarp();  // (lanes leave the loop after different trip counts)
     ss = warp_sum(ss);
     inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
   }

@@ -177,3 +177,39 @@ def test_match_ids_bit_exact():
     assert _Match(get_handle(dev), ids, ids2).info.tolist()[1] == 0
     assert _Match(get_handle(dev), ids, ids2, quick=True).info.tolist() == [0, 0, 4096, 4096]
     assert _Match(get_handle(dev), ids2, ids2, quick=True).info.tolist() == [0, 0, 4096, 4096]  # duplicate id
+
+
+@pytest.mark.parametrize("d", [8, 64, 128, 160, 192, 256, 320, 384, 448, 520, 768, 2048])
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.bfloat16])
+def test_pack_and_unpack_every_width(d, src_dtype):
+    """Row packing (inverse norms) and gradient unpack (positive term + normalise backward) against
+    torch fp32 for widths whose last 256-column group is partly filled: the warp reduction of
+    both kernels must see every column (d % 256 in {32, 64, 96, ...} exercised here)."""
+    from mmlearn_b200._lib import check, ptr
+
+    lib, h, dev, st = _setup()
+    n = 301
+    g = torch.Generator().manual_seed(d)
+    src = (torch.randn(n, d, generator=g) * 1.7).to(src_dtype).to(dev)
+    dt = {torch.float32: 0, torch.bfloat16: 1}[src_dtype]
+    rows = torch.empty(n, d, dtype=torch.bfloat16, device=dev)
+    inv = torch.empty(n, device=dev)
+    check(lib.mmcl_pack_rows(h, ptr(src), dt, n, d, None, n, 1, ptr(rows), ptr(inv), st), "pack")
+    want_inv = 1 / src.float().norm(dim=1)
+    torch.testing.assert_close(inv, want_inv, rtol=1e-5, atol=0)
+    assert torch.equal(rows, src.to(torch.bfloat16))
+    dacc = (torch.randn(n, d, generator=g) * 1e-3).to(dev)
+    partner = torch.randn(n, d, generator=g).to(torch.bfloat16).to(dev)
+    pinv = torch.rand(n, generator=g).to(dev) + 0.5
+    scale = torch.tensor([14.285], device=dev)
+    gout = torch.tensor(0.75, device=dev)
+    out = torch.empty(n, d, dtype=src_dtype, device=dev)
+    weight, pos_coef = 1.3, 2e-4
+    check(lib.mmcl_unpack_grad(h, ptr(dacc), ptr(partner), ptr(pinv), n, d, weight, pos_coef, ptr(gout),
+                               ptr(scale), ptr(src), dt, ptr(inv), 1, None, ptr(out), dt, 1, st), "unpack")
+    torch.cuda.synchronize()
+    gh = weight * 0.75 * 14.285 * (dacc - pos_coef * pinv[:, None] * partner.float())
+    xh = src.float() * want_inv[:, None]
+    want = want_inv[:, None] * (gh - xh * (xh * gh).sum(1, keepdim=True))
+    tol = 1e-5 if src_dtype == torch.float32 else 1e-2
+    assert float((out.float() - want).norm() / want.norm()) < tol

@@ -256,3 +256,28 @@ def test_backward_twice_with_retain_graph():
             assert float(g.float().norm()) > 0
             torch.testing.assert_close(v.grad, g, rtol=0, atol=0)
     assert fn.steady_steps == 2
+
+
+@pytest.mark.parametrize("d", [160, 192, 320, 384])
+def test_widths_with_a_partly_filled_column_group(d):
+    """General path and native step at widths where d % 256 is neither 0, 64 nor 128 (the gradient
+    unpack's warp reduction once dropped columns there)."""
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+
+    n = 384
+    emb, ids = synthetic_inputs(n, d)
+    flags = dict(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    ref = contrastive_oracle(emb, ids, 1 / 0.07, [OPair(("rgb", "text"))], fast_match=True, **flags)
+    fn = ContrastiveLoss(**flags)
+    idt = {k: torch.from_numpy(v).to(DEV) for k, v in ids[0].items()}
+    for step in range(3):
+        leaves = {k: v.to(DEV).clone().requires_grad_(True) for k, v in emb[0].items()}
+        s = torch.tensor(1 / 0.07, device=DEV, requires_grad=True)
+        loss = fn(leaves, idt, s, [LossPairSpec(("rgb", "text"))])
+        loss.backward()
+        torch.cuda.synchronize()
+        _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
+        for k, v in leaves.items():  # tighter than the north-star bound: this is a logic check
+            r = ref.grads[0][k].float()
+            assert float((v.grad.float().cpu() - r).norm() / r.norm()) < 5e-3
+    assert fn.steady_steps == 2
