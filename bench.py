@@ -315,68 +315,84 @@ def main():
     # last step's value is waited for inside the timed region.  ONE event pair spans all K steps
     # (copies, L2 flushes, kernels, read-backs).
     e2e_steps = args.steps
-    out_host = [torch.empty(1 + max(P, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
     main = torch.cuda.current_stream(dev)
     cs = torch.cuda.Stream(dev)
     sets = [dict(emb={m: torch.empty_like(d_emb[m]).requires_grad_(True) for m in mods},
                  ids=torch.empty_like(d_ids),
                  log_s=torch.empty_like(d_log_s).requires_grad_(True),
                  ready=torch.cuda.Event(), done=None) for _ in range(2)]
-    span2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    total = e2e_steps + 2  # two untimed steps first
+    out_host = [torch.empty(1 + max(P, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
 
-    def issue_copy(i):
-        s_ = sets[i % 2]
-        with torch.cuda.stream(cs), torch.no_grad():
-            if s_["done"] is not None:
-                cs.wait_event(s_["done"])  # step i-2 has finished with this buffer set
-            if i == 2:
-                span2[0].record(cs)  # the timed region starts with the first timed step's copy
-            for m in mods:
-                s_["emb"][m].copy_(h_emb[m], non_blocking=True)
-            s_["ids"].copy_(h_ids, non_blocking=True)
-            s_["log_s"].copy_(h_log_s, non_blocking=True)
-            s_["ready"].record(cs)
+    def run_e2e():
+        """One pass of the end-to-end loop; returns (samples/s, host period stats, losses)."""
+        span2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        total = e2e_steps + 2  # two untimed steps first
+        for s_ in sets:
+            s_["done"] = None
 
-    barrier()
-    issue_copy(0)
-    read_ev = [None, None]
-    e2e_losses = []
-    host_t = []
-    host_split["fwd"].clear()
-    host_split["bwd"].clear()
-    for i in range(total):
-        if i + 1 < total:
-            issue_copy(i + 1)
-        s_ = sets[i % 2]
-        flush.fill_(i & 0xFF)
-        main.wait_event(s_["ready"])
-        loss = one_step(s_["emb"], s_["ids"], s_["log_s"])
-        out_host[i % 2].copy_(torch.cat([loss.detach().reshape(1), s_["log_s"].grad.reshape(-1)]),
-                              non_blocking=True)
-        s_["done"] = torch.cuda.Event()
-        s_["done"].record(main)
-        read_ev[i % 2] = s_["done"]
-        if i == total - 1:
-            span2[1].record(main)
-        if i >= 1:  # the host consumes step i-1's loss now (logging lags by one step)
-            read_ev[(i - 1) % 2].synchronize()
-            e2e_losses.append(float(out_host[(i - 1) % 2][0]))
-        host_t.append(time.perf_counter())
-    read_ev[(total - 1) % 2].synchronize()
-    e2e_losses.append(float(out_host[(total - 1) % 2][0]))
-    barrier()
-    t2 = torch.tensor([span2[0].elapsed_time(span2[1])], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = N / (float(t2) / e2e_steps * 1e-3)
-    host_dt = sorted((b_ - a_) * 1e3 for a_, b_ in zip(host_t[2:-1], host_t[3:]))
-    med = lambda v: sorted(v)[len(v) // 2] * 1e3 if v else None  # noqa: E731
-    host_fwd_ms, host_bwd_ms = med(host_split["fwd"][2:]), med(host_split["bwd"][2:])
+        def issue_copy(i):
+            s_ = sets[i % 2]
+            with torch.cuda.stream(cs), torch.no_grad():
+                if s_["done"] is not None:
+                    cs.wait_event(s_["done"])  # step i-2 has finished with this buffer set
+                if i == 2:
+                    span2[0].record(cs)  # the timed region starts with the first timed step's copy
+                for m in mods:
+                    s_["emb"][m].copy_(h_emb[m], non_blocking=True)
+                s_["ids"].copy_(h_ids, non_blocking=True)
+                s_["log_s"].copy_(h_log_s, non_blocking=True)
+                s_["ready"].record(cs)
+
+        barrier()
+        issue_copy(0)
+        read_ev = [None, None]
+        losses, host_t = [], []
+        host_split["fwd"].clear()
+        host_split["bwd"].clear()
+        for i in range(total):
+            if i + 1 < total:
+                issue_copy(i + 1)
+            s_ = sets[i % 2]
+            flush.fill_(i & 0xFF)
+            main.wait_event(s_["ready"])
+            loss_ = one_step(s_["emb"], s_["ids"], s_["log_s"])
+            out_host[i % 2].copy_(torch.cat([loss_.detach().reshape(1),
+                                             s_["log_s"].grad.reshape(-1)]), non_blocking=True)
+            s_["done"] = torch.cuda.Event()
+            s_["done"].record(main)
+            read_ev[i % 2] = s_["done"]
+            if i == total - 1:
+                span2[1].record(main)
+            if i >= 1:  # the host consumes step i-1's loss now (logging lags by one step)
+                read_ev[(i - 1) % 2].synchronize()
+                losses.append(float(out_host[(i - 1) % 2][0]))
+            host_t.append(time.perf_counter())
+        read_ev[(total - 1) % 2].synchronize()
+        losses.append(float(out_host[(total - 1) % 2][0]))
+        barrier()
+        t2 = torch.tensor([span2[0].elapsed_time(span2[1])], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        dt = sorted((b_ - a_) * 1e3 for a_, b_ in zip(host_t[2:-1], host_t[3:]))
+        med = lambda v: sorted(v)[len(v) // 2] * 1e3 if v else None  # noqa: E731
+        host = {"median": dt[len(dt) // 2] if dt else None, "max": dt[-1] if dt else None,
+                "in_forward_call": med(host_split["fwd"][2:]),
+                "in_backward_call": med(host_split["bwd"][2:]),
+                "note": "rank 0's host loop period; a single long step (allocator, page faults) "
+                        "shows up as max >> median"}
+        return N / (float(t2) / e2e_steps * 1e-3), host, losses
+
+    e2e_value, e2e_host, e2e_losses = run_e2e()
+    # the same loop with the opt-in deferred verification (ContrastiveLoss.deferred_verification):
+    # forward() returns without waiting for the device, so the host runs a whole step ahead
+    fn.deferred_verification = True
+    e2e_deferred, e2e_deferred_host, losses_d = run_e2e()
+    fn.deferred_verification = False
+    fn._resolve_deferred()
     h2d = sum(h_emb[m].numel() * 2 for m in mods) + h_ids.numel() * 8 + 4 * max(P, 1)
     d2h = 4 * (1 + max(P, 1))
     e2e_ok = all(math.isfinite(v) and abs(v - loss_value) <= 1e-3 * abs(loss_value)
-                 for v in e2e_losses)
+                 for v in e2e_losses + losses_d)
 
     # ---- (3) parity self-check, outside every timed region, on every rank ----------------------
     # One more step through the same module (so: the same steady-state path that was timed),
@@ -544,12 +560,12 @@ def main():
                        "parallelism": f"dp{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "host_ms_per_step": {"median": host_dt[len(host_dt) // 2] if host_dt else None,
-                                         "max": host_dt[-1] if host_dt else None,
-                                         "in_forward_call": host_fwd_ms,
-                                         "in_backward_call": host_bwd_ms,
-                                         "note": "rank 0's host loop period; a single long step "
-                                                 "(allocator, page faults) shows up as max >> median"},
+                    "host_ms_per_step": e2e_host,
+                    "with_deferred_verification": {
+                        "value": e2e_deferred, "host_ms_per_step": e2e_deferred_host,
+                        "note": "same loop with ContrastiveLoss.deferred_verification = True "
+                                "(opt-in: no host wait inside forward; checked at the end of "
+                                "backward)"},
                     "how": "one event pair over all K steps incl. H2D copies, L2 flushes, kernels "
                            "and the D2H copy of loss + d(log scale) every step; the next step's "
                            "H2D is prefetched on a copy stream (double-buffered inputs); the host "

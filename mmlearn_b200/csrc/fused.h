@@ -63,7 +63,7 @@ struct PushSeg {
 // The tile space is a sequence of PHASES; every CTA takes an equal contiguous share of each phase
 // and walks the phases in order ("local keys of every direction", then "remote keys of direction
 // a", ...), so all SMs work on what is available first.
-constexpr int kMaxFwdPhases = 4;
+constexpr int kMaxFwdPhases = 8;
 struct FwdPhase {
   long long tile_begin, total;
   int tiles_per_cta;
@@ -111,6 +111,10 @@ struct BwdProb {  // one side of one pair: dX = sum_j G_ij yinv_j Y_j
   int nx, ny;
   int nxt, nyt;
   long long tile_begin;  // position in the launch's linear (x tile, d pass, y tile) space
+  long long tiles;       // nxt * ndc * nyt
+  int per_pair;          // tile steps of this problem per CTA pair (every pair takes an equal
+                         // share of every problem, one problem after the other: the problems'
+                         // key matrices then pass through L2 one at a time)
   int map_x, map_y256, map_y64;
   const float* scale;
   const float* xinv;
@@ -135,9 +139,9 @@ struct BwdProb {  // one side of one pair: dX = sum_j G_ij yinv_j Y_j
 struct BwdLaunch {
   int nprob, d, kchunks, ndc, dp, dcc;
   long long total;
-  int per_pair;
+  int pairs;             // CTA pairs of the launch
   int accumulate;        // 1: red.add into dx (caller zero-fills); 0: stores + scratch (below)
-  float* scratch;        // [cta pairs][128][dp] fp32: head segments that continue an item
+  float* scratch;        // [problem][cta pair][128][dp] fp32: head segments that continue an item
   // several ranks: off_col of remote sources becomes valid when flags[kChanLse][r] >= seq
   int world, rank;
   const unsigned long long* flags;

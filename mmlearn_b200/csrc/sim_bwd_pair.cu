@@ -287,9 +287,14 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_acc = tmem, tm_s = tmem + 256;
 
-  const long long t_begin = (long long)pair * L.per_pair;
-  long long t_end = t_begin + L.per_pair;
-  if (t_end > L.total) t_end = L.total;
+  // this pair's share [t_begin, t_end) of problem pi
+  auto prob_range = [&](int pi, long long* t_begin, long long* t_end) {
+    const BwdProb& P = L.prob[pi];
+    *t_begin = P.tile_begin + (long long)pair * P.per_pair;
+    long long e = *t_begin + P.per_pair;
+    if (e > P.tile_begin + P.tiles) e = P.tile_begin + P.tiles;
+    *t_end = e;
+  };
   const int nb = L.dcc / BK;  // 64-wide column boxes of this CTA's dX slice
 
   if (warp == 0) {
@@ -320,9 +325,11 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         }
       };
       bool pend = false;
-      int pend_yt = 0, pi = 0;
+      int pend_yt = 0;
+      for (int pi = 0; pi < L.nprob; ++pi) {
+      long long t_begin, t_end;
+      prob_range(pi, &t_begin, &t_end);
       for (long long t = t_begin; t < t_end; ++t) {
-        pi = find_prob(L, t, pi);
         const BwdProb& p = L.prob[pi];
         tmX = &maps.tm[p.map_x];
         tmY256 = &maps.tm[p.map_y256];
@@ -343,6 +350,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           pend_yt = yt;
         }
         if (seg_last && pend) { load_dx(col0, pend_yt); pend = false; }
+      }
       }
     }
   } else if (warp == 1) {
@@ -428,9 +436,10 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         ++peer_cnt;
       };
       bool pend = false;
-      int pi = 0;
+      for (int pi = 0; pi < L.nprob; ++pi) {
+      long long t_begin, t_end;
+      prob_range(pi, &t_begin, &t_end);
       for (long long t = t_begin; t < t_end; ++t) {
-        pi = find_prob(L, t, pi);
         const int nyt = L.prob[pi].nyt;
         const int yt = int((t - L.prob[pi].tile_begin) % nyt);
         const bool own = (uint32_t(t - t_begin) & 1u) == c;
@@ -449,6 +458,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           ++seg;
         }
       }
+      }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
@@ -462,10 +472,11 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
     const uint32_t sw = uint32_t(row & 7);
     uint32_t own_cnt = 0, seg = 0;
-    int pi = 0;
     bool seg_head = false;  // the current segment continues an item another CTA pair started
+    for (int pi = 0; pi < L.nprob; ++pi) {
+    long long t_begin, t_end;
+    prob_range(pi, &t_begin, &t_end);
     for (long long t = t_begin; t < t_end; ++t) {
-      pi = find_prob(L, t, pi);
       const BwdProb& p = L.prob[pi];
       const long long local = t - p.tile_begin;
       const long long item = local / p.nyt;
@@ -619,7 +630,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           } else if (seg_head) {
             // continuation of an item another pair started: this pair's scratch tile
             float4* dst = reinterpret_cast<float4*>(
-                L.scratch + ((long long)pair * BM + row) * L.dp + int(c) * L.dcc + ch * 32);
+                L.scratch + (((long long)pi * L.pairs + pair) * BM + row) * L.dp + int(c) * L.dcc +
+                ch * 32);
 #pragma unroll
             for (int e = 0; e < 32; e += 4)
               dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
@@ -638,6 +650,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         ++seg;
         seg_head = false;
       }
+    }
     }
   }
   __syncwarp();
@@ -677,22 +690,29 @@ int bwd_add_prob(BwdLaunch* L, long long nx, long long ny) {
   p.nyt = int((ny + BNY - 1) / BNY);
   p.tile_begin = L->total;
   p.off_mul = 1.f;
-  L->total += (long long)p.nxt * L->ndc * p.nyt;
+  p.tiles = (long long)p.nxt * L->ndc * p.nyt;
+  L->total += p.tiles;
   return L->nprob++;
 }
 
 // Fixes the split over CTA pairs; returns the scratch bytes an accumulate == 0 launch needs.
 size_t bwd_finish(BwdLaunch* L, int num_sms) {
+  long long widest = 1;
+  for (int i = 0; i < L->nprob; ++i)
+    if (L->prob[i].tiles > widest) widest = L->prob[i].tiles;
   long long pairs = num_sms / 2;
-  if (L->total < pairs) pairs = L->total;
+  if (widest < pairs) pairs = widest;
   if (pairs < 1) pairs = 1;
-  L->per_pair = int((L->total + pairs - 1) / pairs);
-  if (L->per_pair < 1) L->per_pair = 1;
-  pairs = (L->total + L->per_pair - 1) / L->per_pair;
-  return size_t(pairs) * BM * size_t(L->dp) * sizeof(float);
+  L->pairs = int(pairs);
+  for (int i = 0; i < L->nprob; ++i) {
+    BwdProb& p = L->prob[i];
+    p.per_pair = int((p.tiles + pairs - 1) / pairs);
+    if (p.per_pair < 1) p.per_pair = 1;
+  }
+  return size_t(L->nprob) * size_t(pairs) * BM * size_t(L->dp) * sizeof(float);
 }
 
-int bwd_cta_pairs(const BwdLaunch& L) { return int((L.total + L.per_pair - 1) / L.per_pair); }
+int bwd_cta_pairs(const BwdLaunch& L) { return L.pairs; }
 
 int bwd_make_maps(TensorMaps* maps, int slot, const void* rows, long long n, long long d) {
   if (slot < 0 || 3 * slot + 2 >= kMaxBwdMaps) return -1;

@@ -257,7 +257,7 @@ sim_lse_fwd_kernel(const __grid_constant__ TensorMaps maps, const __grid_constan
         const PushSeg& sg = L.push[sgi];
         const long long units = (long long)(sg.bytes >> 4);
         const uint4* src = reinterpret_cast<const uint4*>(src_base + sg.off);
-        constexpr int U = 4;
+        constexpr int U = 8;  // 8 x 512 B per warp in flight before the 7-peer store burst
         for (long long base = w * (32 * U); base < units; base += nw * (32 * U)) {
           uint4 v[U];
 #pragma unroll

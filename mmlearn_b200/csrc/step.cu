@@ -334,7 +334,10 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
   bool plan_ok = true;
   for (int p = 0; p < s->P && plan_ok; ++p)
     for (int dir = 0; dir < 2; ++dir) {
-      const int k = fwd_add_sub(&s->fwd, s->rows, s->N, split ? kt_lo : 0, split ? n_local : -1, 0);
+      // (one rank: every (pair, direction) is its own phase, so one key matrix at a time streams
+      // through L2; several ranks: phase 0 holds the local key blocks of all of them)
+      const int k = fwd_add_sub(&s->fwd, s->rows, s->N, split ? kt_lo : 0, split ? n_local : -1,
+                                split ? 0 : p * 2 + dir);
       plan_ok = plan_ok && k >= 0;
       s->sub_idx[(p * 2 + dir) * 2] = k;
     }
@@ -820,10 +823,8 @@ int mmcl_step_backward(mmcl_step* s, int parity, const void* const* emb, const f
   UL.normalize = s->normalize;
   UL.rows = b;
   UL.gout = gout;
-  UL.scratch = s->pair_bwd ? reinterpret_cast<const float*>(v.ws + s->off_scratch) : nullptr;
   UL.ndc = s->bwd.ndc;
   UL.dp = s->bwd.dp;
-  UL.per_pair = s->bwd.per_pair;
   int k = 0, bk = 0;
   for (int p = 0; p < s->P; ++p) {
     const mmcl_step_pair& pr = s->pairs[p];
@@ -849,8 +850,13 @@ int mmcl_step_backward(mmcl_step* s, int parity, const void* const* emb, const f
       q.direct = grad_direct[mx] ? 1 : 0;
       q.grad_dtype = grad_direct[mx] ? s->dtype[mx] : MMCL_F32;
       q.blocks = int((b + 3) / 4);
-      q.tile_begin = s->pair_bwd ? s->bwd.prob[this_bk].tile_begin : 0;
+      q.tile_begin = 0;
       q.nyt = s->pair_bwd ? s->bwd.prob[this_bk].nyt : 1;
+      q.per_pair = s->pair_bwd ? s->bwd.prob[this_bk].per_pair : 1;
+      q.scratch = s->pair_bwd
+                      ? reinterpret_cast<const float*>(v.ws + s->off_scratch) +
+                            size_t(this_bk) * size_t(s->bwd.pairs) * 128 * size_t(s->bwd.dp)
+                      : nullptr;
     }
   }
   UL.nprob = k;

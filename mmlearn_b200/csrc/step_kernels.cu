@@ -465,13 +465,13 @@ __global__ void step_unpack_kernel(const __grid_constant__ UnpackLaunch L) {
     float pa[8];
     float4 a0 = __ldcg(reinterpret_cast<const float4*>(P.dacc + row * d + cc));
     float4 a1 = __ldcg(reinterpret_cast<const float4*>(P.dacc + row * d + cc + 4));
-    if (L.scratch) {
+    if (P.scratch) {
       // segments of this (x tile, d pass) item that other CTA pairs continued
       const int dc = cc / L.dp, cin = cc - dc * L.dp;
-      const long long t0 = P.tile_begin + ((long long)xt * L.ndc + dc) * P.nyt;
-      const long long c_first = t0 / L.per_pair, c_last = (t0 + P.nyt - 1) / L.per_pair;
+      const long long t0 = ((long long)xt * L.ndc + dc) * P.nyt;
+      const long long c_first = t0 / P.per_pair, c_last = (t0 + P.nyt - 1) / P.per_pair;
       for (long long cp = c_first + 1; cp <= c_last; ++cp) {
-        const float* sp = L.scratch + ((cp * 128 + rin) * (long long)L.dp + cin);
+        const float* sp = P.scratch + ((cp * 128 + rin) * (long long)L.dp + cin);
         const float4 b0 = __ldcg(reinterpret_cast<const float4*>(sp));
         const float4 b1 = __ldcg(reinterpret_cast<const float4*>(sp + 4));
         a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;

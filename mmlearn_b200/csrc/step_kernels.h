@@ -100,16 +100,16 @@ struct UnpackProb {
   float weight, pos_coef;
   int src_dtype, grad_dtype, direct;
   int blocks;
-  long long tile_begin;  // of the matching backward problem
-  int nyt;
+  long long tile_begin;  // of the matching backward problem (relative to its own start: 0)
+  int nyt, per_pair;
+  const float* scratch;  // that problem's scratch tiles ([cta pair][128][dp]) or null
 };
 
 struct UnpackLaunch {
   int nprob, d, normalize;
   long long rows;
   const float* gout;
-  const float* scratch;  // backward scratch tiles or null
-  int ndc, dp, per_pair;
+  int ndc, dp;
   UnpackProb prob[kMaxBwdProbs];
 };
 
