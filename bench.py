@@ -15,6 +15,7 @@ two fused similarity/LSE passes, two fused recompute-backward passes, gradient u
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -278,6 +279,11 @@ def main():
         sampler.start()  # before warm-up: nvidia-smi needs ~100 ms to deliver its first sample
     for _ in range(warmup):
         one_step(d_emb, d_ids, d_log_s)
+    # A full (generation-2) garbage collection of a process that has imported torch takes tens of
+    # milliseconds -- a hundred 1 ms steps.  As training loops that care about step-time jitter
+    # do, the collector is run now and kept off inside the timed regions.
+    gc.collect()
+    gc.disable()
     barrier()
     sampler.mark()
     l0 = lib.mmcl_kernel_launches()
@@ -389,6 +395,7 @@ def main():
     e2e_deferred, e2e_deferred_host, losses_d = run_e2e()
     fn.deferred_verification = False
     fn._resolve_deferred()
+    gc.enable()
     h2d = sum(h_emb[m].numel() * 2 for m in mods) + h_ids.numel() * 8 + 4 * max(P, 1)
     d2h = 4 * (1 + max(P, 1))
     e2e_ok = all(math.isfinite(v) and abs(v - loss_value) <= 1e-3 * abs(loss_value)
@@ -441,11 +448,61 @@ def main():
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     # ---- (4) dominant kernel alone (recompute backward), CUDA events on its stream ------------
-    # Same entry point and the same kind of arguments the step uses: raw bf16 rows + inverse
-    # norms, and the REAL log-sum-exp vectors of this problem (computed here by the forward
-    # kernel), so the kernel takes whichever exponential path the data selects.
+    # The launch the step itself issues: one more steady-state forward without the eager backward,
+    # then the step's fused backward launch (every (pair, side) problem in one
+    # sim_grad_bwd_pair_kernel launch, `mmcl_step_grad_kernels`) timed on its own with CUDA events,
+    # L2 flushed before every launch.  It reads this step's real log-sum-exp vectors, so it takes
+    # whichever exponential path the data selects.  (With several ranks the call would need the
+    # peers in lock step; the roofline entry is a one-GPU measurement.)
     roof = None
-    if rank == 0:
+    if rank == 0 and world == 1:
+        fn.eager_backward = False
+        loss = fn({f"{m}_embedding": d_emb[m] for m in mods}, {m: d_ids for m in mods},
+                  d_log_s.exp(), pairs)
+        run = getattr(loss.grad_fn, "run", None)
+        fast = getattr(run, "fast", None)
+        kms, sides = None, 2 * P
+        if fast is not None:
+            sp, parity, es_, ws_ = fast
+            st = torch.cuda.current_stream(dev).cuda_stream
+            reps = max(5, min(args.steps, 20))
+            kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(reps)]
+            for i in range(reps + 2):
+                flush.fill_(i & 0xFF)
+                torch.cuda.synchronize()
+                if i >= 2:
+                    kev[i - 2][0].record()
+                sp.grad_kernels(parity, run.scale, ws_, st)
+                if i >= 2:
+                    kev[i - 2][1].record()
+            torch.cuda.synchronize()
+            kms = sum(e0.elapsed_time(e1) for e0, e1 in kev) / reps
+        loss.backward()
+        fn.eager_backward = True
+        if kms is not None:
+            flops = 4.0 * b * N * d * sides  # two of the reference's four backward GEMMs per side
+            achieved = flops / (kms * 1e-3) / 1e12
+            peak = float(peaks["bf16_tflops"])
+            traffic, traffic_src = ncu_traffic("sim_grad_bwd_pair_kernel", b, N, d)
+            step_tf = 12.0 * b * N * d * P / (ms_per_step * 1e-3) / 1e12
+            roof = {"bound": "tensor",
+                    "kernel": "sim_grad_bwd_pair_kernel (the step's fused launch: "
+                              f"{sides} (pair, side) problems)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic * sides if traffic else None, "traffic_source": traffic_src,
+                    "algorithmic_bytes": ((b + N) * d * 2 + b * d * 4) * sides,
+                    "ms_per_launch": kms, "peak_source": f"{peaks['_source']} burst cuBLAS bf16",
+                    "timed": "mmcl_step_grad_kernels on the step's own saved state, L2 flushed "
+                             "before every launch",
+                    "step_tflops": step_tf, "step_frac_of_burst": step_tf / peak,
+                    "step_frac_of_sustained": step_tf / float(peaks["bf16_tflops_sustained"]),
+                    "executed_mma_flops_per_step": 12.0 * b * N * d * P,
+                    "algorithmic_flops_per_step": 12.0 * b * N * d * P}
+
+    if rank == 0 and world > 1:
+        # several ranks: one side of the pair through the ABI entry point (same kernel, one
+        # problem, accumulate mode), rank 0 alone, on this rank's share of the batch
         hnd = get_handle(dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         ma, mb = pair_cfg[0][0], pair_cfg[0][1]
@@ -480,18 +537,15 @@ def main():
                 kev[i - 2][1].record()
         torch.cuda.synchronize()
         kms = sum(e0.elapsed_time(e1) for e0, e1 in kev) / reps
-        flops = 4.0 * b * N * d  # two of the reference's four backward GEMMs per launch
-        achieved = flops / (kms * 1e-3) / 1e12
+        achieved = 4.0 * b * N * d / (kms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops"])
-        traffic, traffic_src = ncu_traffic("sim_grad_bwd_pair_kernel", b, N, d)
         step_tf = 12.0 * b * N * d * P / (ms_per_step * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "sim_grad_bwd_pair_kernel", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src,
-                "algorithmic_bytes": (b + N) * d * 2 + b * d * 4,
+        roof = {"bound": "tensor", "kernel": "sim_grad_bwd_pair_kernel (one side, ABI call)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes": (b + N) * d * 2 + b * d * 4,
                 "ms_per_launch": kms, "peak_source": f"{peaks['_source']} burst cuBLAS bf16",
-                "timed": "mmcl_sim_grad_bwd_lse (the step's entry point) with this problem's own "
-                         "log-sum-exp vectors, L2 flushed before every launch",
+                "timed": "mmcl_sim_grad_bwd_lse (memset + kernel) on rank 0's share with this "
+                         "problem's own log-sum-exp vectors, L2 flushed before every launch",
                 "step_tflops": step_tf, "step_frac_of_burst": step_tf / peak,
                 "step_frac_of_sustained": step_tf / float(peaks["bf16_tflops_sustained"]),
                 "executed_mma_flops_per_step": 12.0 * b * N * d * P,
@@ -557,6 +611,8 @@ def main():
                        "rows_per_gpu": b, "l2": "flushed between timed iterations (256 MiB fill kernel on the stream, "
                              "outside each iteration's event pair; no host sync between iterations)",
                        "ms_per_step_incl_flush": ms_per_step_with_flush,
+                       "gc": "Python's cyclic garbage collector is run before and disabled inside "
+                             "the timed regions",
                        "parallelism": f"dp{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,

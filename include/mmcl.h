@@ -97,8 +97,9 @@ int mmcl_pack_rows(mmcl_handle* h, const void* src, int src_dtype, int64_t src_r
  * ROWS rank r contributes / receives; rows are `row_bytes` wide.  Uneven counts are supported
  * (grouped broadcasts / reduces).  world == 1: a device-to-device copy.
  * Replaces: _gather_dicts / _gather_all_tensors / _simple_gather_all_tensors at
- * contrastive.py:431-578 (all-gather, and the reduce-scatter that autograd's all-gather
- * performs in backward, contrastive.py:506).
+ * contrastive.py:431-578 (all-gather).  The reduce-scatter that autograd's all-gather performs
+ * in backward (contrastive.py:506) has no counterpart: every rank forms the complete gradient of
+ * its own rows, so no [N, d] gradient crosses NVLink.
  * ------------------------------------------------------------------------------------------ */
 /* ------------------------------------------------------------------------------------------
  * Symmetric peer-memory arena (one node, CUDA IPC over NVLink / NVSwitch): the B200-native
@@ -140,8 +141,6 @@ int mmcl_group_start(mmcl_handle* h);
 int mmcl_group_end(mmcl_handle* h);
 int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int64_t* counts,
                          int64_t row_bytes, mmcl_stream stream);
-int mmcl_reduce_scatter_rows_f32(mmcl_handle* h, const float* send, float* recv,
-                                 const int64_t* counts, int64_t row_floats, mmcl_stream stream);
 int mmcl_all_reduce_sum_f32(mmcl_handle* h, float* buf, int64_t n, mmcl_stream stream);
 
 /* ------------------------------------------------------------------------------------------

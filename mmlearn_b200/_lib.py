@@ -73,8 +73,6 @@ SYMBOLS = {
     "mmcl_group_end": (c_int, [c_void_p]),
     "mmcl_all_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64,
                                      c_void_p]),
-    "mmcl_reduce_scatter_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64),
-                                             c_int64, c_void_p]),
     "mmcl_all_reduce_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "mmcl_sim_lse_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64, c_int64]),
     "mmcl_sim_lse_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,

@@ -272,48 +272,6 @@ int mmcl_all_gather_rows(mmcl_handle* h, const void* send, void* recv, const int
   return MMCL_OK;
 }
 
-int mmcl_reduce_scatter_rows_f32(mmcl_handle* h, const float* send, float* recv,
-                                 const int64_t* counts, int64_t row_floats, mmcl_stream stream) {
-  REQUIRE(h && counts && row_floats > 0, "mmcl_reduce_scatter_rows_f32: bad arguments");
-  std::lock_guard<std::mutex> lk(h->mu);
-  DeviceGuard g(h->device);
-  auto st = static_cast<cudaStream_t>(stream);
-  if (h->world == 1) {
-    if (counts[0] > 0 && send != recv) {
-      cudaError_t e = cudaMemcpyAsync(recv, send, size_t(counts[0]) * row_floats * 4,
-                                      cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) return cuda_fail(e, "mmcl_reduce_scatter_rows_f32");
-    }
-    return MMCL_OK;
-  }
-  bool even = true;
-  for (int r = 1; r < h->world; ++r) even = even && counts[r] == counts[0];
-  ncclResult_t r;
-  if (even) {
-    r = ncclReduceScatter(send, recv, size_t(counts[0]) * row_floats, ncclFloat, ncclSum, h->comm,
-                          st);
-    if (r != ncclSuccess) return nccl_fail(r, "ncclReduceScatter");
-    return MMCL_OK;
-  }
-  r = ncclGroupStart();
-  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
-  size_t off = 0;
-  for (int root = 0; root < h->world; ++root) {
-    const size_t n = size_t(counts[root]) * row_floats;
-    if (n > 0) {
-      r = ncclReduce(send + off, recv, n, ncclFloat, ncclSum, root, h->comm, st);
-      if (r != ncclSuccess) {
-        ncclGroupEnd();
-        return nccl_fail(r, "ncclReduce");
-      }
-    }
-    off += n;
-  }
-  r = ncclGroupEnd();
-  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
-  return MMCL_OK;
-}
-
 int mmcl_all_reduce_sum_f32(mmcl_handle* h, float* buf, int64_t n, mmcl_stream stream) {
   REQUIRE(h && (n == 0 || buf), "mmcl_all_reduce_sum_f32: bad arguments");
   if (h->world == 1 || n == 0) return MMCL_OK;
