@@ -463,7 +463,7 @@ def main():
         fast = getattr(run, "fast", None)
         kms, sides = None, 2 * P
         if fast is not None:
-            sp, parity, es_, ws_ = fast
+            sp, buf_parity, es_, ws_ = fast
             st = torch.cuda.current_stream(dev).cuda_stream
             reps = max(5, min(args.steps, 20))
             kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -473,7 +473,7 @@ def main():
                 torch.cuda.synchronize()
                 if i >= 2:
                     kev[i - 2][0].record()
-                sp.grad_kernels(parity, run.scale, ws_, st)
+                sp.grad_kernels(buf_parity, run.scale, ws_, st)
                 if i >= 2:
                     kev[i - 2][1].record()
             torch.cuda.synchronize()
