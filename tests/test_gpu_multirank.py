@@ -284,3 +284,60 @@ def test_retrieval_recall_two_ranks():
     for r in range(2):
         assert np.array_equal(ret[r]["hits5"], np.concatenate([h for h, _ in per_rank[r]]))
         assert np.array_equal(ret[r]["ranks"], np.concatenate([q for _, q in per_rank[r]]))
+
+
+def _worker_rows(rank, world, rows, d, init_file, ret):
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world,
+                            device_id=dev)
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+    from oracle.contrastive_oracle import synthetic_inputs
+
+    emb, ids = synthetic_inputs(rows * world, d, world=world)
+    fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    outs = []
+    for _ in range(3):
+        leaves = {k: v.to(dev).requires_grad_(True) for k, v in emb[rank].items()}
+        s = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+        loss = fn(leaves, {k: torch.from_numpy(v).to(dev) for k, v in ids[rank].items()}, s,
+                  [LossPairSpec(("rgb", "text"))])
+        loss.backward()
+        torch.cuda.synchronize()
+        outs.append({"loss": float(loss.detach()), "dscale": float(s.grad),
+                     "steady_steps": fn.steady_steps,
+                     **{f"grad_{k}": v.grad.float().cpu().numpy() for k, v in leaves.items()}})
+    ret[rank] = outs
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rows,d,want_steady", [(18, 64, [0, 0, 0]), (264, 128, [0, 1, 2])])
+def test_row_counts_around_the_fused_step_limits_two_ranks(rows, d, want_steady):
+    """rows % 4 != 0: the fused multi-rank step (16-byte peer stores) refuses the shape and every
+    rank stays on the general path; rows = 264 (not a multiple of the 256-key tile, so key tiles
+    straddle the two ranks' blocks): native steps.  Both against the oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle.contrastive_oracle import LossPairSpec as OPair
+    from oracle.contrastive_oracle import contrastive_oracle, synthetic_inputs
+
+    emb, ids = synthetic_inputs(rows * 2, d, world=2)
+    ref = contrastive_oracle(emb, ids, 1 / 0.07, [OPair(("rgb", "text"))], l2_normalize=True,
+                             local_loss=True, gather_with_grad=True, fast_match=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_rows, args=(2, rows, d, os.path.join(td, "init"), ret), nprocs=2, join=True)
+    for r in range(2):
+        assert [o["steady_steps"] for o in ret[r]] == want_steady
+        for o in ret[r]:
+            assert o["loss"] == pytest.approx(ref.losses[r], rel=1e-3)
+            for k in ("rgb_embedding", "text_embedding"):
+                g, e = torch.from_numpy(o[f"grad_{k}"]), ref.grads[r][k].float()
+                assert float(g.norm()) == pytest.approx(float(e.norm()), rel=1e-2)
+                assert float(torch.nn.functional.cosine_similarity(g.flatten(), e.flatten(), dim=0)) > 0.999

@@ -191,3 +191,25 @@ def test_deferred_verification():
         fn(e, bad, sc, [LossPairSpec(("rgb", "text"))])  # native step on a batch that does not fit
         with pytest.raises(RuntimeError, match="deferred_verification"):
             fn(e, good, sc, [LossPairSpec(("rgb", "text"))])
+
+
+def test_more_pairs_than_the_fused_step_handles_stay_on_the_general_path():
+    """Four modalities / six pairs exceed the fused step's limits (4 pairs): the plug-in keeps
+    using the general path (same numbers, no native steps)."""
+    from mmlearn_b200 import ContrastiveLoss, Modalities
+
+    for m in ("dna",):
+        if not Modalities.has_modality(m):
+            Modalities.register_modality(m)
+    mods = ("rgb", "dna", "text", "audio")
+    emb, ids = synthetic_inputs(256, 128, modalities=mods)
+    pairs = [(a, b, 1.0 + 0.1 * i) for i, (a, b) in enumerate(
+        (x, y) for k, x in enumerate(mods) for y in mods[k + 1:])]
+    assert len(pairs) == 6
+    ref = contrastive_oracle(emb, ids, 1 / 0.07, [OPair((a, b), w) for a, b, w in pairs],
+                             l2_normalize=True, fast_match=True)
+    fn = ContrastiveLoss(l2_normalize=True)
+    for _ in range(3):
+        loss, leaves, s = _step(fn, emb[0], ids[0], 1 / 0.07, pairs, torch.bfloat16)
+        _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
+    assert fn.steady_steps == 0
