@@ -87,12 +87,6 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-// problem that holds linear tile t (t only grows: `s` is carried along)
-__device__ __forceinline__ int find_prob(const BwdLaunch& L, long long t, int s) {
-  while (s + 1 < L.nprob && t >= L.prob[s + 1].tile_begin) ++s;
-  return s;
-}
-
 // 16 logits of one row -> 8 packed bf16x2 values of G.  Exact form (see sim_bwd.cu):
 // cy[e] = (off_col[j], 1/||y_j||).
 template <int MODE>

@@ -716,7 +716,6 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
       s->n_post_launches += 1;
       QL.ticket_target = s->n_post_launches * (unsigned long long)s->post_total_blocks;
       QL.seq = s->seq;
-      bool any_lse = false;
       for (int p = 0; p < s->P; ++p) {
         const mmcl_step_pair& pr = s->pairs[p];
         PostPair& pp = QL.pair[p];
@@ -733,7 +732,6 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         pp.lse_off[1] = s->po[p].lse_all[1];
         pp.range = reinterpret_cast<float*>(v.ws + s->po[p].range);
         pp.range_off = s->po[p].range_all;
-        any_lse = any_lse || pp.push_lse;
       }
       if (W > 1) {
         QL.peers = h->arena.d_peers;
@@ -742,7 +740,6 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         QL.status_ok = status_ok;
         QL.release_lse = s->need_grad ? 1 : 0;
       }
-      (void)any_lse;
       int nk = 0;
       for (int m = 0; m < s->M; ++m)
         if (s->is_key[m]) {
