@@ -122,3 +122,32 @@ def test_config4_three_modalities_full_size():
                            atol=1e-6 + 2e-3 * np.asarray(gross))
         del ref_leaves, hat, total
     assert fn.steady_steps == 1
+
+
+def test_config3_shape_through_the_module():
+    """Config 3's width (d = 1024: two 512-column passes of the backward kernel, query tiles not
+    resident in shared memory in the forward kernel) through the drop-in module, general path and
+    native step, at N = 16384 on one GPU, against the chunked fp32 checker that bench.py uses for
+    the full-size 8-GPU run (tools/chunked_check.py)."""
+    from mmlearn_b200 import ContrastiveLoss, LossPairSpec
+    from tools.chunked_check import compare, rank_check
+
+    n, d, s = 16384, 1024, 1 / 0.07
+    g = torch.Generator().manual_seed(1234)
+    xa = torch.randn(n, d, generator=g)
+    xb = 0.5 * xa + torch.randn(n, d, generator=g)
+    full = {"rgb": xa.to(torch.bfloat16).to(DEV), "text": xb.to(torch.bfloat16).to(DEV)}
+    ref = rank_check(full, [("rgb", "text", 1.0, s)], 0, 1)
+    ids = torch.stack([torch.zeros(n, dtype=torch.long), torch.arange(n)], 1).to(DEV)
+    fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    for step in range(2):
+        leaves = {m: full[m].clone().requires_grad_(True) for m in full}
+        sc = torch.tensor(s, device=DEV, requires_grad=True)
+        loss = fn({f"{m}_embedding": leaves[m] for m in leaves}, {"rgb": ids, "text": ids}, sc,
+                  [LossPairSpec(("rgb", "text"))])
+        loss.backward()
+        torch.cuda.synchronize()
+        c = compare(ref, float(loss.detach()), [float(sc.grad)], {m: leaves[m].grad for m in leaves})
+        assert c["loss_rel"] < 1e-3 and c["grad_rel"] < 1e-2 and c["dscale_rel"] < 1e-2
+        assert c["grad_cos_min"] > 0.999
+    assert fn.steady_steps == 1
