@@ -45,11 +45,19 @@ namespace {
 constexpr int BM = 128;
 constexpr int BNY = 256;
 constexpr int BK = 64;
+#ifdef MMCL_X_RING4  // timing experiment (with MMCL_NO_X): four 32 KB slots instead of three 48 KB
+constexpr int XCHUNK_BYTES = 0;
+#else
 constexpr int XCHUNK_BYTES = BM * BK * 2;              // 16 KB
+#endif
 constexpr int YBOX_BYTES = BNY * BK * 2;               // 32 KB
 constexpr int YSUB_BYTES = 64 * BK * 2;                // 8 KB: one [64 y, 64 d] box
 constexpr int STAGE_BYTES = XCHUNK_BYTES + YBOX_BYTES; // 48 KB
+#ifdef MMCL_X_RING4
+constexpr int NSTAGES = 4;
+#else
 constexpr int NSTAGES = 3;
+#endif
 constexpr int ATOM_BYTES = BM * 128;                   // 16 KB: 128 rows x 64 keys (bf16)
 constexpr int STG_BYTES = 4 * ATOM_BYTES;              // 64 KB: G tile 128 x 256 (bf16)
 constexpr int XFER_BYTES = 8 * 2048;                   // per epilogue warp: 32 rows x 64 B
@@ -58,23 +66,62 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float kFastRange = 40.f;
 
 #ifdef MMCL_TRACE
-// timeline instrumentation (tools/bwd_trace.cu): (event, step, globaltimer ns) for pair 0
-__device__ unsigned long long g_trace[2][4096][2];
-__device__ unsigned int g_trace_n[2];
-__device__ __forceinline__ void trace_ev(int pair, uint32_t cta, unsigned ev, unsigned step) {
-  if (pair != 0) return;
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  const unsigned i = atomicAdd(&g_trace_n[cta], 1u);
-  if (i < 4096) {
-    g_trace[cta][i][0] = (static_cast<unsigned long long>(ev) << 32) | step;
-    g_trace[cta][i][1] = t;
-  }
+// Timeline instrumentation (tools/bwd_trace.cu): (event, step, SM clock) of one CTA pair.  Every
+// tracing thread (role: 0 TMA producer, 1 MMA issuer, 2/3 first lane of the two epilogue
+// warpgroups) appends to its own buffer with a register index -- no atomics, so a stamp costs a
+// clock read and two stores and the traced pair stays representative.
+#ifndef MMCL_TRACE_PAIR
+#define MMCL_TRACE_PAIR 0
+#endif
+constexpr unsigned kTraceCap = 8192;
+__device__ unsigned long long g_trace[2][4][kTraceCap][2];
+__device__ __forceinline__ void trace_ev(int pair, uint32_t cta, int role, unsigned& i, unsigned ev,
+                                         unsigned step) {
+  if (pair != MMCL_TRACE_PAIR || i >= kTraceCap) return;
+  g_trace[cta][role][i][0] = (static_cast<unsigned long long>(ev) << 32) | step;
+  g_trace[cta][role][i][1] = clock64();
+  ++i;
 }
-#define TRACE(ev, step) trace_ev(pair, c, ev, unsigned(step))
+#define TRACE(ev, step) trace_ev(pair, c, trace_role, trace_i, ev, unsigned(step))
 #else
 #define TRACE(ev, step)
 #endif
+#if defined(MMCL_TRACE) && defined(MMCL_TRACE_FINE)  // stamps inside the conversion loop
+#define TRACE_EPI(k) if (lane == 0 && q == 0) TRACE(32 + ci * 8 + (k), own_cnt)
+#else
+#define TRACE_EPI(k)
+#endif
+
+// (x tile, d pass, y tile) of consecutive linear tiles of one problem: one 64-bit division at the
+// start of a range, increments after it
+struct TileWalk {
+  int xt = 0, dc = 0, yt = 0;
+#ifdef MMCL_WALK_DIV  // timing experiment only: the per-tile divisions this struct replaced
+  long long loc = 0;
+#endif
+  __device__ __forceinline__ void start(long long local, int nyt, int ndc) {
+#ifdef MMCL_WALK_DIV
+    loc = local;
+#endif
+    const long long item = local / nyt;
+    yt = int(local - item * nyt);
+    xt = int(item / ndc);
+    dc = int(item - (long long)xt * ndc);
+  }
+  __device__ __forceinline__ void next(int nyt, int ndc) {
+#ifdef MMCL_WALK_DIV
+    start(++loc, nyt, ndc);
+    return;
+#endif
+    if (++yt == nyt) {
+      yt = 0;
+      if (++dc == ndc) {
+        dc = 0;
+        ++xt;
+      }
+    }
+  }
+};
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -116,11 +163,19 @@ __device__ __forceinline__ void conv16_fast(const uint32_t (&v)[16], uint32_t* g
   const float2 c2 = make_float2(c, c), o2 = make_float2(-offr, -offr), r2 = make_float2(R, R);
 #pragma unroll
   for (int e = 0; e < 16; e += 2) {
+#ifdef MMCL_X_NO_LDS  // timing experiments only (tools/bwd_trace.cu), wrong results
+    const float4 f = make_float4(c, offr, R, c);
+#else
     const float4 f = cy4[e >> 1];
+#endif
     const float2 yi = make_float2(f.z, f.w);
     const float2 t = __fmul2_rn(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), yi);
     const float2 l = __ffma2_rn(t, c2, o2);
+#ifdef MMCL_X_NO_MUFU
+    const float2 ex = l;
+#else
     const float2 ex = make_float2(ex2f(l.x), ex2f(l.y));
+#endif
     const float2 w = __ffma2_rn(r2, make_float2(f.x, f.y), yi);
     const float2 gg = __fmul2_rn(ex, w);
     g[e >> 1] = pack_bf16x2(gg.x, gg.y);
@@ -183,8 +238,18 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
   float* s_range = reinterpret_cast<float*>(s_full + 10);  // [16] lo per warp, [16] hi per warp
   float* s_mu = s_range + 32;                              // [kMaxBwdProbs] centre of the offsets
   int* s_fast = reinterpret_cast<int*>(s_mu + kMaxBwdProbs);  // [kMaxBwdProbs] one-exponential form
+  // hand-off of a G chunk from epilogue warp w to the send warps: written / read out of sXfer[w]
+  uint64_t* xf_full = reinterpret_cast<uint64_t*>(s_fast + kMaxBwdProbs);  // [8]
+  uint64_t* xf_free = xf_full + 8;                                          // [8]
+#ifdef MMCL_TRACE_MMA_WAIT
+  uint64_t* dbg_bar = xf_free + 8;
+#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MMCL_TRACE
+  unsigned trace_i = 0;
+  const int trace_role = warp < 2 ? warp : 2 + ((warp - 4) >> 2);
+#endif
   const uint32_t c = cluster_ctarank();
   const uint32_t peer = c ^ 1u;
   const int pair = blockIdx.x >> 1;
@@ -200,6 +265,13 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     mbar_init(stg_free, 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 256);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&xf_full[i], 1);
+      mbar_init(&xf_free[i], 1);
+    }
+#ifdef MMCL_TRACE_MMA_WAIT
+    mbar_init(dbg_bar, 1);
+#endif
     fence_barrier_init();
   }
   if (L.world > 1 && int(threadIdx.x) < L.world && int(threadIdx.x) != L.rank) {
@@ -297,25 +369,37 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       int stage = 0;
       uint32_t phase = 0;
       const CUtensorMap *tmX = nullptr, *tmY256 = nullptr, *tmY64 = nullptr;
+#ifdef MMCL_TRACE
+      unsigned prod_cnt = 0;
+#endif
       auto load_s = [&](int xt, int yt) {
+        TRACE(56, prod_cnt);
         for (int kc = 0; kc < L.kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (kc == 0 || kc == 3) TRACE(kc == 0 ? 8 : 9, prod_cnt);
+#ifdef MMCL_NO_X  // timing experiment only (tools/bwd_trace.cu): X chunks not streamed, wrong results
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES - XCHUNK_BYTES);
+          uint8_t* dst = sStage + stage * STAGE_BYTES;
+#else
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* dst = sStage + stage * STAGE_BYTES;
           tma_load_2d(dst, tmX, kc * BK, xt * BM, &full[stage]);
+#endif
           tma_load_2d(dst + XCHUNK_BYTES, tmY256, kc * BK, yt * BNY, &full[stage]);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       };
-      auto load_dx = [&](int col0, int yt) {
+      auto load_dx = [&](int col0, int yt, int kind) {
         for (int js = 0; js < BNY / 64; ++js) {
           mbar_wait(&empty[stage], phase ^ 1);
+          TRACE(24 + kind * 4 + js, prod_cnt);
           mbar_arrive_expect_tx(&full[stage], nb * YSUB_BYTES);
           uint8_t* dst = sStage + stage * STAGE_BYTES;
           for (int b = 0; b < nb; ++b)
             tma_load_2d(dst + b * YSUB_BYTES, tmY64, col0 + b * BK, yt * BNY + js * 64,
                         &full[stage]);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          TRACE(52 + js, prod_cnt * 2 + kind);
         }
       };
       bool pend = false;
@@ -323,27 +407,29 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       for (int pi = 0; pi < L.nprob; ++pi) {
       long long t_begin, t_end;
       prob_range(pi, &t_begin, &t_end);
-      for (long long t = t_begin; t < t_end; ++t) {
-        const BwdProb& p = L.prob[pi];
-        tmX = &maps.tm[p.map_x];
-        tmY256 = &maps.tm[p.map_y256];
-        tmY64 = &maps.tm[p.map_y64];
-        const long long local = t - p.tile_begin;
-        const long long item = local / p.nyt;
-        const int yt = int(local % p.nyt);
-        const int xt = int(item / L.ndc), dc = int(item % L.ndc);
+      const BwdProb& p = L.prob[pi];
+      tmX = &maps.tm[p.map_x];
+      tmY256 = &maps.tm[p.map_y256];
+      tmY64 = &maps.tm[p.map_y64];
+      TileWalk w;
+      if (t_begin < t_end) w.start(t_begin - p.tile_begin, p.nyt, L.ndc);
+      for (long long t = t_begin; t < t_end; ++t, w.next(p.nyt, L.ndc)) {
+        const int yt = w.yt, xt = w.xt, dc = w.dc;
         const int col0 = dc * L.dp + int(c) * L.dcc;
         const bool own = (uint32_t(t - t_begin) & 1u) == c;
         const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
         if (own) {
           load_s(xt, yt);
-          if (pend) { load_dx(col0, pend_yt); pend = false; }
-          load_dx(col0, yt);
+#ifdef MMCL_TRACE
+          ++prod_cnt;
+#endif
+          if (pend) { load_dx(col0, pend_yt, 0); pend = false; }
+          load_dx(col0, yt, 1);
         } else {
           pend = true;
           pend_yt = yt;
         }
-        if (seg_last && pend) { load_dx(col0, pend_yt); pend = false; }
+        if (seg_last && pend) { load_dx(col0, pend_yt, 0); pend = false; }
       }
       }
     }
@@ -355,11 +441,15 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       const uint32_t stg = smem_u32(sStg);
       int stage = 0;
       uint32_t phase = 0, own_cnt = 0, peer_cnt = 0, seg = 0, accf = 0;
+#ifdef MMCL_TRACE_MMA_WAIT
+      uint32_t dbg_cnt = 0;
+#endif
       auto issue_s = [&]() {
         TRACE(0, own_cnt);
         for (int kc = 0; kc < L.kchunks; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          TRACE(16 + kc, own_cnt);
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
@@ -386,6 +476,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           if ((js & 1) == 0) TRACE(5 + (js >> 1), own_cnt);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          TRACE(40 + js, own_cnt);
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -394,6 +485,12 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
             accf = 1;
           }
           umma_commit(&empty[stage]);
+#ifdef MMCL_TRACE_MMA_WAIT  // timing experiment: how long do the 4 MMAs of a quarter take to complete?
+          umma_commit(dbg_bar);
+          mbar_wait(dbg_bar, dbg_cnt & 1);
+          ++dbg_cnt;
+          TRACE(48 + js, own_cnt);
+#endif
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
         TRACE(7, own_cnt);
@@ -404,6 +501,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         TRACE(2, peer_cnt);
 #ifdef MMCL_NO_DSM  // timing experiment only (tools/bwd_trace.cu): no G exchange, wrong results
         mbar_arrive_expect_tx(stg_full, 8 * 8 * 16);
+#elif defined(MMCL_X_PLAIN)
+        mbar_arrive_expect_tx(stg_full, 8 * 4 * 16);
 #else
         mbar_arrive_expect_tx(stg_full, STG_BYTES);  // 128 rows x 512 B from the partner's st.async
 #endif
@@ -414,6 +513,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         for (int js = 0; js < BNY / 64; ++js) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          TRACE(44 + js, peer_cnt);
           const uint32_t st = smem_u32(sStage + stage * STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -433,9 +533,11 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       for (int pi = 0; pi < L.nprob; ++pi) {
       long long t_begin, t_end;
       prob_range(pi, &t_begin, &t_end);
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int nyt = L.prob[pi].nyt;
-        const int yt = int((t - L.prob[pi].tile_begin) % nyt);
+      const int nyt = L.prob[pi].nyt;
+      TileWalk w;
+      if (t_begin < t_end) w.start(t_begin - L.prob[pi].tile_begin, nyt, L.ndc);
+      for (long long t = t_begin; t < t_end; ++t, w.next(nyt, L.ndc)) {
+        const int yt = w.yt;
         const bool own = (uint32_t(t - t_begin) & 1u) == c;
         const bool seg_last = (t == t_end - 1) || (yt == nyt - 1);
         if (own) {
@@ -454,6 +556,62 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       }
       }
     }
+#ifndef MMCL_SEND_INLINE
+  } else if (warp < 4) {
+    // ================================ G send warps ================================
+    // Warp 2 serves epilogue warps 4-7, warp 3 serves 8-11: per chunk it waits for the warp's 2 KB
+    // buffer, reads it back transposed (the buffer is free again as soon as the values are in
+    // registers) and stores it into the partner's staging tile (128-byte swizzle, K-major): each
+    // st.async covers 8 rows x 64 contiguous bytes -- distributed-shared-memory stores are
+    // packet-rate bound.
+    const int wg = warp - 2;
+    const uint32_t peer_base = mapa_shared(smem_u32(sStg), peer);
+    const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
+    uint32_t own_cnt = 0, xf_cnt = 0;
+    for (int pi = 0; pi < L.nprob; ++pi) {
+    long long t_begin, t_end;
+    prob_range(pi, &t_begin, &t_end);
+    for (long long t = t_begin; t < t_end; ++t) {
+      if ((uint32_t(t - t_begin) & 1u) != c) continue;
+      // the partner has finished reading the G tile stored two steps ago (write-after-read on its
+      // staging buffer; nothing is read here, so CTA-scope acquire is enough)
+      mbar_wait(stg_free, (own_cnt & 1) ^ 1);
+      ++own_cnt;
+#pragma unroll 1
+      for (int ci = 0; ci < 4; ++ci) {
+        const int ch = ci * 2 + wg;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const int ew = wg * 4 + q;  // epilogue warp 4 + ew: lane quadrant q, key half wg
+          const uint32_t xb = smem_u32(sXfer) + uint32_t(ew) * 2048u;
+          mbar_wait(&xf_full[ew], xf_cnt & 1);
+          uint32_t w[4][4];
+#pragma unroll
+          for (int s2 = 0; s2 < 4; ++s2)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[s2][0]), "=r"(w[s2][1]), "=r"(w[s2][2]), "=r"(w[s2][3])
+                         : "r"(xb + uint32_t(s2 * 512 + lane * 16))
+                         : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xf_free[ew]);
+          const uint32_t abase =
+              peer_base + uint32_t(q * 32) * 128u + uint32_t(ch >> 1) * ATOM_BYTES;
+#pragma unroll
+          for (int s2 = 0; s2 < 4; ++s2) {
+            const uint32_t r = uint32_t(s2 * 8 + (lane >> 2));  // row within the warp's 32 rows
+            const uint32_t half = (uint32_t(ch) ^ (r >> 2)) & 1u;
+#ifdef MMCL_NO_DSM
+            if (s2 == 0 && ci == 0 && lane < 8)  // 8 warps x 8 lanes x 16 B: timing experiment only
+#endif
+            st_async_v4(abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4), w[s2][0],
+                        w[s2][1], w[s2][2], w[s2][3], peer_stg_full);
+          }
+        }
+        ++xf_cnt;
+      }
+    }
+    }
+#endif
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
     const int wg = (warp - 4) >> 2;  // key half this warpgroup converts
@@ -465,17 +623,16 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     const uint32_t xb = smem_u32(sXfer) + uint32_t(warp - 4) * 2048u;
     const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
     const uint32_t sw = uint32_t(row & 7);
-    uint32_t own_cnt = 0, seg = 0;
+    uint32_t own_cnt = 0, seg = 0, xf_cnt = 0;
     bool seg_head = false;  // the current segment continues an item another CTA pair started
     for (int pi = 0; pi < L.nprob; ++pi) {
     long long t_begin, t_end;
     prob_range(pi, &t_begin, &t_end);
-    for (long long t = t_begin; t < t_end; ++t) {
-      const BwdProb& p = L.prob[pi];
-      const long long local = t - p.tile_begin;
-      const long long item = local / p.nyt;
-      const int yt = int(local % p.nyt);
-      const int xt = int(item / L.ndc), dc = int(item % L.ndc);
+    const BwdProb& p = L.prob[pi];
+    TileWalk w;
+    if (t_begin < t_end) w.start(t_begin - p.tile_begin, p.nyt, L.ndc);
+    for (long long t = t_begin; t < t_end; ++t, w.next(p.nyt, L.ndc)) {
+      const int yt = w.yt, xt = w.xt, dc = w.dc;
       const bool own = (uint32_t(t - t_begin) & 1u) == c;
       const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
       const int grow = xt * BM + row;
@@ -531,7 +688,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         if (lane == 0 && q == 0) TRACE(10 + wg, own_cnt);
         // the partner has finished reading the G tile I stored two steps ago (write-after-read
         // on its staging buffer; nothing is read here, so CTA-scope acquire is enough)
+#ifdef MMCL_SEND_INLINE
         mbar_wait(stg_free, (own_cnt & 1) ^ 1);
+#endif
         if (lane == 0 && q == 0) TRACE(12 + wg, own_cnt);
         // Conversion order: step ci converts the 64-key quarter ci (32-column chunk 2*ci by
         // warpgroup 0, chunk 2*ci+1 by warpgroup 1) and hands it to the MMA issuer at once, so the
@@ -558,11 +717,14 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         for (int ci = 0; ci < 4; ++ci) {
           const int ch = ci * 2 + wg;
           tmem_ld_wait();
+          TRACE_EPI(0);
           tmem_ld_x16(sbase + ch * 32 + 16, vb);
           convert(va, g, ch * 32);
+          TRACE_EPI(1);
           tmem_ld_wait();
           if (ci < 3) tmem_ld_x16(sbase + ((ci + 1) * 2 + wg) * 32, va);
           convert(vb, g + 8, ch * 32 + 16);
+          TRACE_EPI(2);
           // G chunk ch overwrites the first 16 columns of S chunk ch (already consumed by this
           // very thread), so no other warp's reads are ever at risk
           tmem_st_x16(tm_s + lane_base + ch * 32, g);
@@ -571,7 +733,10 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           // warp first transposes through a 2 KB buffer: each st.async instruction then covers
           // 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
           const uint32_t j0 = uint32_t(ch & 1) * 4u;
-          __syncwarp();  // the previous chunk has been read out of the buffer
+#ifndef MMCL_SEND_INLINE
+          // hand the chunk to the send warps (warps 2-3): they read it back transposed and issue
+          // the st.async stream, so its back-pressure never stalls the conversion
+          mbar_wait(&xf_free[warp - 4], (xf_cnt & 1) ^ 1);
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             const uint32_t a = xb + uint32_t(lane) * 64u + ((((j0 + qd) ^ sw) & 3u) << 4);
@@ -580,6 +745,52 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
                          : "memory");
           }
           __syncwarp();
+          if (lane == 0) mbar_arrive(&xf_full[warp - 4]);
+          ++xf_cnt;
+          TRACE_EPI(3);
+#else
+          __syncwarp();  // the previous chunk has been read out of the buffer
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const uint32_t a = xb + uint32_t(lane) * 64u + ((((j0 + qd) ^ sw) & 3u) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(g[4 * qd]),
+                         "r"(g[4 * qd + 1]), "r"(g[4 * qd + 2]), "r"(g[4 * qd + 3])
+                         : "memory");
+          }
+#if defined(MMCL_X_BULK)  // timing experiment only: one 2 KB bulk copy per warp and chunk (wrong layout)
+          fence_proxy_async_smem();
+          __syncwarp();
+          TRACE_EPI(3);
+          if (lane == 0)
+            asm volatile(
+                "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], "
+                "%2, [%3];" ::"r"(mapa_shared(smem_u32(sStg), peer) + uint32_t(ch * 4 + q) * 2048u),
+                "r"(xb), "r"(2048u), "r"(peer_stg_full)
+                : "memory");
+#elif defined(MMCL_X_PLAIN)  // timing experiment only: plain remote stores + 16 B of st.async per warp
+          __syncwarp();
+          TRACE_EPI(3);
+          {
+            const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {
+              const uint32_t r = uint32_t(s2 * 8 + (lane >> 2));
+              const uint32_t half = (uint32_t(ch) ^ (r >> 2)) & 1u;
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(xb + uint32_t(s2 * 512 + lane * 16))
+                           : "memory");
+              const uint32_t dst = abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4);
+              asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0),
+                           "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
+              if (s2 == 3 && lane == 0) st_async_v4(dst, w0, w1, w2, w3, peer_stg_full);
+            }
+          }
+#else
+          __syncwarp();
+          TRACE_EPI(3);
           const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
 #pragma unroll
           for (int s2 = 0; s2 < 4; ++s2) {
@@ -596,10 +807,14 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
             st_async_v4(abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4), w0, w1, w2, w3,
                         peer_stg_full);
           }
+#endif
+#endif
           // this warpgroup's share of quarter ci is in tensor memory
+          TRACE_EPI(4);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&g_full[ci]);
+          TRACE_EPI(5);
         }
         if (lane == 0 && q == 0) TRACE(14 + wg, own_cnt);
         ++own_cnt;

@@ -1,6 +1,8 @@
-// Timeline of the pair backward kernel: builds sim_bwd_pair.cu with MMCL_TRACE and prints, for
-// pair 0, the globaltimer stamps of the MMA issuer and the epilogue warpgroups per step.
+// Timeline of the pair backward kernel: builds sim_bwd_pair.cu with MMCL_TRACE and dumps, for one
+// CTA pair, the SM-clock stamps of the TMA producer, the MMA issuer and the epilogue warpgroups
+// per step (CSV: cta,event,step,clk), plus the launch time.  tools/bwd_trace_summary.py reads it.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/bwd_trace tools/bwd_trace.cu
+//   tools/bin/bwd_trace [out.csv]
 #define MMCL_TRACE 1
 #include <cstdio>
 #include <vector>
@@ -24,9 +26,8 @@ int main(int argc, char** argv) {
   float sc = 14.285f; cudaMemcpy(scale, &sc, 4, cudaMemcpyHostToDevice);
   cudaMemset(dx, 0, nx * d * 4);
   const char* err = nullptr;
-  for (int rep = 0; rep < 3; ++rep) {
-    unsigned zero[2] = {0, 0};
-    cudaMemcpyToSymbol(mmcl::g_trace_n, zero, sizeof(zero));
+  for (int rep = 0; rep < 5; ++rep) {
+    void* tp; cudaGetSymbolAddress(&tp, mmcl::g_trace); cudaMemset(tp, 0, sizeof(mmcl::g_trace));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
     cudaError_t e = mmcl::launch_sim_grad_bwd_pair(148, x, nx, y, ny, d, scale, nullptr, nullptr, offr, offc, 1.f, 0.f, 0.f, dx, 0, &err);
@@ -35,21 +36,16 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("rep %d: launch %s sync %s  %.3f ms\n", rep, cudaGetErrorString(e), cudaGetErrorString(e2), ms);
   }
-  static unsigned long long tr[2][4096][2]; unsigned n[2];
-  cudaMemcpyFromSymbol(tr, mmcl::g_trace, sizeof(tr)); cudaMemcpyFromSymbol(n, mmcl::g_trace_n, sizeof(n));
-  unsigned long long t0 = ~0ull;
-  for (int c = 0; c < 2; ++c) for (unsigned i = 0; i < std::min(n[c], 4096u); ++i) t0 = std::min(t0, tr[c][i][1]);
-  const char* names[16] = {"S.issue", "S.issued", "dXp.wait", "dXp.go", "dXp.issued", "dXo.h0", "dXo.h1", "dXo.issued", "", "", "epi0.S", "epi1.S", "epi0.free", "epi1.free", "epi0.done", "epi1.done"};
-  for (int c = 0; c < 2; ++c) {
-    printf("---- CTA %d: %u events\n", c, n[c]);
-    std::vector<std::pair<unsigned long long, unsigned long long>> ev;
-    for (unsigned i = 0; i < std::min(n[c], 4096u); ++i) ev.push_back({tr[c][i][1], tr[c][i][0]});
-    std::sort(ev.begin(), ev.end());
-    int shown = 0;
-    for (auto& e : ev) {
-      unsigned evid = unsigned(e.second >> 32), step = unsigned(e.second & 0xffffffff);
-      if (step >= 20 && step < 26) { printf("  t=%8llu ns  %-10s step %u\n", e.first - t0, names[evid & 15], step); ++shown; }
-    }
-  }
+  static unsigned long long tr[2][4][mmcl::kTraceCap][2];
+  cudaMemcpyFromSymbol(tr, mmcl::g_trace, sizeof(tr));
+  FILE* f = fopen(argc > 1 ? argv[1] : "bwd_trace.csv", "w");
+  fprintf(f, "cta,event,step,clk\n");
+  unsigned n = 0;
+  for (int c = 0; c < 2; ++c)
+    for (int r = 0; r < 4; ++r)
+      for (unsigned i = 0; i < mmcl::kTraceCap && tr[c][r][i][1]; ++i, ++n)
+        fprintf(f, "%d,%u,%u,%llu\n", c, unsigned(tr[c][r][i][0] >> 32), unsigned(tr[c][r][i][0] & 0xffffffffu), tr[c][r][i][1]);
+  fclose(f);
+  printf("events: %u\n", n);
   return 0;
 }

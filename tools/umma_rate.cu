@@ -109,7 +109,7 @@ int main() {
   const int iters = 2048;
   for (int ctas : {148})
     for (int a_tmem = 0; a_tmem < 2; ++a_tmem)
-      for (int b_mn = 0; b_mn < 1; ++b_mn)
+      for (int b_mn = 0; b_mn < 2; ++b_mn)
         for (int N : {64, 128, 256}) {
           for (int nacc : {1, 2}) {
           rate_kernel<<<ctas, 128, smem_bytes>>>(N, a_tmem, b_mn, 64, d_cyc, nacc);  // warm
