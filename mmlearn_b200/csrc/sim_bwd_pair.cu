@@ -45,19 +45,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BNY = 256;
 constexpr int BK = 64;
-#ifdef MMCL_X_RING4  // timing experiment (with MMCL_NO_X): four 32 KB slots instead of three 48 KB
-constexpr int XCHUNK_BYTES = 0;
-#else
 constexpr int XCHUNK_BYTES = BM * BK * 2;              // 16 KB
-#endif
 constexpr int YBOX_BYTES = BNY * BK * 2;               // 32 KB
 constexpr int YSUB_BYTES = 64 * BK * 2;                // 8 KB: one [64 y, 64 d] box
 constexpr int STAGE_BYTES = XCHUNK_BYTES + YBOX_BYTES; // 48 KB
-#ifdef MMCL_X_RING4
-constexpr int NSTAGES = 4;
-#else
 constexpr int NSTAGES = 3;
-#endif
 constexpr int ATOM_BYTES = BM * 128;                   // 16 KB: 128 rows x 64 keys (bf16)
 constexpr int STG_BYTES = 4 * ATOM_BYTES;              // 64 KB: G tile 128 x 256 (bf16)
 constexpr int XFER_BYTES = 8 * 2048;                   // per epilogue warp: 32 rows x 64 B
@@ -96,23 +88,13 @@ __device__ __forceinline__ void trace_ev(int pair, uint32_t cta, int role, unsig
 // start of a range, increments after it
 struct TileWalk {
   int xt = 0, dc = 0, yt = 0;
-#ifdef MMCL_WALK_DIV  // timing experiment only: the per-tile divisions this struct replaced
-  long long loc = 0;
-#endif
   __device__ __forceinline__ void start(long long local, int nyt, int ndc) {
-#ifdef MMCL_WALK_DIV
-    loc = local;
-#endif
     const long long item = local / nyt;
     yt = int(local - item * nyt);
     xt = int(item / ndc);
     dc = int(item - (long long)xt * ndc);
   }
   __device__ __forceinline__ void next(int nyt, int ndc) {
-#ifdef MMCL_WALK_DIV
-    start(++loc, nyt, ndc);
-    return;
-#endif
     if (++yt == nyt) {
       yt = 0;
       if (++dc == ndc) {
@@ -163,19 +145,11 @@ __device__ __forceinline__ void conv16_fast(const uint32_t (&v)[16], uint32_t* g
   const float2 c2 = make_float2(c, c), o2 = make_float2(-offr, -offr), r2 = make_float2(R, R);
 #pragma unroll
   for (int e = 0; e < 16; e += 2) {
-#ifdef MMCL_X_NO_LDS  // timing experiments only (tools/bwd_trace.cu), wrong results
-    const float4 f = make_float4(c, offr, R, c);
-#else
     const float4 f = cy4[e >> 1];
-#endif
     const float2 yi = make_float2(f.z, f.w);
     const float2 t = __fmul2_rn(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), yi);
     const float2 l = __ffma2_rn(t, c2, o2);
-#ifdef MMCL_X_NO_MUFU
-    const float2 ex = l;
-#else
     const float2 ex = make_float2(ex2f(l.x), ex2f(l.y));
-#endif
     const float2 w = __ffma2_rn(r2, make_float2(f.x, f.y), yi);
     const float2 gg = __fmul2_rn(ex, w);
     g[e >> 1] = pack_bf16x2(gg.x, gg.y);
@@ -241,9 +215,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
   // hand-off of a G chunk from epilogue warp w to the send warps: written / read out of sXfer[w]
   uint64_t* xf_full = reinterpret_cast<uint64_t*>(s_fast + kMaxBwdProbs);  // [8]
   uint64_t* xf_free = xf_full + 8;                                          // [8]
-#ifdef MMCL_TRACE_MMA_WAIT
-  uint64_t* dbg_bar = xf_free + 8;
-#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef MMCL_TRACE
@@ -269,9 +240,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       mbar_init(&xf_full[i], 1);
       mbar_init(&xf_free[i], 1);
     }
-#ifdef MMCL_TRACE_MMA_WAIT
-    mbar_init(dbg_bar, 1);
-#endif
     fence_barrier_init();
   }
   if (L.world > 1 && int(threadIdx.x) < L.world && int(threadIdx.x) != L.rank) {
@@ -377,14 +345,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         for (int kc = 0; kc < L.kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (kc == 0 || kc == 3) TRACE(kc == 0 ? 8 : 9, prod_cnt);
-#ifdef MMCL_NO_X  // timing experiment only (tools/bwd_trace.cu): X chunks not streamed, wrong results
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES - XCHUNK_BYTES);
-          uint8_t* dst = sStage + stage * STAGE_BYTES;
-#else
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* dst = sStage + stage * STAGE_BYTES;
           tma_load_2d(dst, tmX, kc * BK, xt * BM, &full[stage]);
-#endif
           tma_load_2d(dst + XCHUNK_BYTES, tmY256, kc * BK, yt * BNY, &full[stage]);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -413,11 +376,12 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       tmY64 = &maps.tm[p.map_y64];
       TileWalk w;
       if (t_begin < t_end) w.start(t_begin - p.tile_begin, p.nyt, L.ndc);
-      for (long long t = t_begin; t < t_end; ++t, w.next(p.nyt, L.ndc)) {
+      const int n = int(t_end - t_begin), nyt = p.nyt, ndc = L.ndc;
+      for (int i = 0; i < n; ++i, w.next(nyt, ndc)) {
         const int yt = w.yt, xt = w.xt, dc = w.dc;
         const int col0 = dc * L.dp + int(c) * L.dcc;
-        const bool own = (uint32_t(t - t_begin) & 1u) == c;
-        const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
+        const bool own = (uint32_t(i) & 1u) == c;
+        const bool seg_last = (i == n - 1) || (yt == nyt - 1);
         if (own) {
           load_s(xt, yt);
 #ifdef MMCL_TRACE
@@ -441,9 +405,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       const uint32_t stg = smem_u32(sStg);
       int stage = 0;
       uint32_t phase = 0, own_cnt = 0, peer_cnt = 0, seg = 0, accf = 0;
-#ifdef MMCL_TRACE_MMA_WAIT
-      uint32_t dbg_cnt = 0;
-#endif
       auto issue_s = [&]() {
         TRACE(0, own_cnt);
         for (int kc = 0; kc < L.kchunks; ++kc) {
@@ -485,12 +446,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
             accf = 1;
           }
           umma_commit(&empty[stage]);
-#ifdef MMCL_TRACE_MMA_WAIT  // timing experiment: how long do the 4 MMAs of a quarter take to complete?
-          umma_commit(dbg_bar);
-          mbar_wait(dbg_bar, dbg_cnt & 1);
-          ++dbg_cnt;
-          TRACE(48 + js, own_cnt);
-#endif
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
         TRACE(7, own_cnt);
@@ -501,8 +456,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         TRACE(2, peer_cnt);
 #ifdef MMCL_NO_DSM  // timing experiment only (tools/bwd_trace.cu): no G exchange, wrong results
         mbar_arrive_expect_tx(stg_full, 8 * 8 * 16);
-#elif defined(MMCL_X_PLAIN)
-        mbar_arrive_expect_tx(stg_full, 8 * 4 * 16);
 #else
         mbar_arrive_expect_tx(stg_full, STG_BYTES);  // 128 rows x 512 B from the partner's st.async
 #endif
@@ -536,10 +489,10 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       const int nyt = L.prob[pi].nyt;
       TileWalk w;
       if (t_begin < t_end) w.start(t_begin - L.prob[pi].tile_begin, nyt, L.ndc);
-      for (long long t = t_begin; t < t_end; ++t, w.next(nyt, L.ndc)) {
-        const int yt = w.yt;
-        const bool own = (uint32_t(t - t_begin) & 1u) == c;
-        const bool seg_last = (t == t_end - 1) || (yt == nyt - 1);
+      const int n = int(t_end - t_begin), ndc = L.ndc;
+      for (int i = 0; i < n; ++i, w.next(nyt, ndc)) {
+        const bool own = (uint32_t(i) & 1u) == c;
+        const bool seg_last = (i == n - 1) || (w.yt == nyt - 1);
         if (own) {
           issue_s();
           if (pend) { issue_dx_peer(); pend = false; }
@@ -556,7 +509,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       }
       }
     }
-#ifndef MMCL_SEND_INLINE
   } else if (warp < 4) {
     // ================================ G send warps ================================
     // Warp 2 serves epilogue warps 4-7, warp 3 serves 8-11: per chunk it waits for the warp's 2 KB
@@ -571,8 +523,9 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     for (int pi = 0; pi < L.nprob; ++pi) {
     long long t_begin, t_end;
     prob_range(pi, &t_begin, &t_end);
-    for (long long t = t_begin; t < t_end; ++t) {
-      if ((uint32_t(t - t_begin) & 1u) != c) continue;
+    const int n = int(t_end - t_begin);
+    for (int i = 0; i < n; ++i) {
+      if ((uint32_t(i) & 1u) != c) continue;
       // the partner has finished reading the G tile stored two steps ago (write-after-read on its
       // staging buffer; nothing is read here, so CTA-scope acquire is enough)
       mbar_wait(stg_free, (own_cnt & 1) ^ 1);
@@ -611,7 +564,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       }
     }
     }
-#endif
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
     const int wg = (warp - 4) >> 2;  // key half this warpgroup converts
@@ -619,9 +571,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128 - wg * 128;  // 0..127 within the warpgroup
     const uint32_t lane_base = uint32_t(q * 32) << 16;
-    const uint32_t peer_stg = mapa_shared(smem_u32(sStg), peer) + uint32_t(q * 32) * 128u;
     const uint32_t xb = smem_u32(sXfer) + uint32_t(warp - 4) * 2048u;
-    const uint32_t peer_stg_full = mapa_shared(smem_u32(stg_full), peer);
     const uint32_t sw = uint32_t(row & 7);
     uint32_t own_cnt = 0, seg = 0, xf_cnt = 0;
     bool seg_head = false;  // the current segment continues an item another CTA pair started
@@ -631,12 +581,13 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
     const BwdProb& p = L.prob[pi];
     TileWalk w;
     if (t_begin < t_end) w.start(t_begin - p.tile_begin, p.nyt, L.ndc);
-    for (long long t = t_begin; t < t_end; ++t, w.next(p.nyt, L.ndc)) {
+    const int n = int(t_end - t_begin);
+    for (int i = 0; i < n; ++i, w.next(p.nyt, L.ndc)) {
       const int yt = w.yt, xt = w.xt, dc = w.dc;
-      const bool own = (uint32_t(t - t_begin) & 1u) == c;
-      const bool seg_last = (t == t_end - 1) || (yt == p.nyt - 1);
+      const bool own = (uint32_t(i) & 1u) == c;
+      const bool seg_last = (i == n - 1) || (yt == p.nyt - 1);
       const int grow = xt * BM + row;
-      if (t == t_begin) seg_head = yt != 0;
+      if (i == 0) seg_head = yt != 0;
       const int mode = p.bce ? 4 : ((p.off_row ? 1 : 0) | (p.off_col ? 2 : 0));
       const bool fast = s_fast[pi] != 0;
       const float mu = s_mu[pi];
@@ -686,11 +637,6 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         mbar_wait(s_full, own_cnt & 1);
         tc_fence_after();
         if (lane == 0 && q == 0) TRACE(10 + wg, own_cnt);
-        // the partner has finished reading the G tile I stored two steps ago (write-after-read
-        // on its staging buffer; nothing is read here, so CTA-scope acquire is enough)
-#ifdef MMCL_SEND_INLINE
-        mbar_wait(stg_free, (own_cnt & 1) ^ 1);
-#endif
         if (lane == 0 && q == 0) TRACE(12 + wg, own_cnt);
         // Conversion order: step ci converts the 64-key quarter ci (32-column chunk 2*ci by
         // warpgroup 0, chunk 2*ci+1 by warpgroup 1) and hands it to the MMA issuer at once, so the
@@ -728,14 +674,15 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           // G chunk ch overwrites the first 16 columns of S chunk ch (already consumed by this
           // very thread), so no other warp's reads are ever at risk
           tmem_st_x16(tm_s + lane_base + ch * 32, g);
-          // The same 32 keys (64 B per row) go to the partner's staging tile (atom ch/2, 128-byte
-          // swizzle, K-major).  Distributed-shared-memory stores are packet-rate bound, so the
-          // warp first transposes through a 2 KB buffer: each st.async instruction then covers
-          // 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
+          // this warpgroup's share of quarter ci is in tensor memory: hand it to the MMA issuer
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&g_full[ci]);
+          TRACE_EPI(3);
+          // ... and the same 32 keys (64 B per row) to the send warps (warps 2-3) through this warp's
+          // 2 KB buffer: they read it back transposed and issue the st.async stream, so its
+          // back-pressure never stalls the conversion
           const uint32_t j0 = uint32_t(ch & 1) * 4u;
-#ifndef MMCL_SEND_INLINE
-          // hand the chunk to the send warps (warps 2-3): they read it back transposed and issue
-          // the st.async stream, so its back-pressure never stalls the conversion
           mbar_wait(&xf_free[warp - 4], (xf_cnt & 1) ^ 1);
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
@@ -747,74 +694,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           __syncwarp();
           if (lane == 0) mbar_arrive(&xf_full[warp - 4]);
           ++xf_cnt;
-          TRACE_EPI(3);
-#else
-          __syncwarp();  // the previous chunk has been read out of the buffer
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const uint32_t a = xb + uint32_t(lane) * 64u + ((((j0 + qd) ^ sw) & 3u) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(g[4 * qd]),
-                         "r"(g[4 * qd + 1]), "r"(g[4 * qd + 2]), "r"(g[4 * qd + 3])
-                         : "memory");
-          }
-#if defined(MMCL_X_BULK)  // timing experiment only: one 2 KB bulk copy per warp and chunk (wrong layout)
-          fence_proxy_async_smem();
-          __syncwarp();
-          TRACE_EPI(3);
-          if (lane == 0)
-            asm volatile(
-                "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], "
-                "%2, [%3];" ::"r"(mapa_shared(smem_u32(sStg), peer) + uint32_t(ch * 4 + q) * 2048u),
-                "r"(xb), "r"(2048u), "r"(peer_stg_full)
-                : "memory");
-#elif defined(MMCL_X_PLAIN)  // timing experiment only: plain remote stores + 16 B of st.async per warp
-          __syncwarp();
-          TRACE_EPI(3);
-          {
-            const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
-#pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2) {
-              const uint32_t r = uint32_t(s2 * 8 + (lane >> 2));
-              const uint32_t half = (uint32_t(ch) ^ (r >> 2)) & 1u;
-              uint32_t w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                           : "r"(xb + uint32_t(s2 * 512 + lane * 16))
-                           : "memory");
-              const uint32_t dst = abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4);
-              asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0),
-                           "r"(w1), "r"(w2), "r"(w3)
-                           : "memory");
-              if (s2 == 3 && lane == 0) st_async_v4(dst, w0, w1, w2, w3, peer_stg_full);
-            }
-          }
-#else
-          __syncwarp();
-          TRACE_EPI(3);
-          const uint32_t abase = peer_stg + uint32_t(ch >> 1) * ATOM_BYTES;
-#pragma unroll
-          for (int s2 = 0; s2 < 4; ++s2) {
-            const uint32_t r = uint32_t(s2 * 8 + (lane >> 2));  // row within the warp's 32 rows
-            const uint32_t half = (uint32_t(ch) ^ (r >> 2)) & 1u;
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                         : "r"(xb + uint32_t(s2 * 512 + lane * 16))
-                         : "memory");
-#ifdef MMCL_NO_DSM
-            if (s2 == 0 && ci == 0 && lane < 8)  // 8 warps x 8 lanes x 16 B: timing experiment only
-#endif
-            st_async_v4(abase + r * 128u + half * 64u + (uint32_t(lane & 3) << 4), w0, w1, w2, w3,
-                        peer_stg_full);
-          }
-#endif
-#endif
-          // this warpgroup's share of quarter ci is in tensor memory
           TRACE_EPI(4);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&g_full[ci]);
-          TRACE_EPI(5);
         }
         if (lane == 0 && q == 0) TRACE(14 + wg, own_cnt);
         ++own_cnt;
