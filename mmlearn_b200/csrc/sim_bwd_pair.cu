@@ -231,11 +231,11 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       mbar_init(&empty[i], 1);
     }
     mbar_init(s_full, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&g_full[i], 256);
+    for (int i = 0; i < 4; ++i) mbar_init(&g_full[i], 8);  // one arrival per epilogue warp
     mbar_init(stg_full, 1);  // armed with expect_tx by the MMA issuer; bytes arrive via st.async
     mbar_init(stg_free, 1);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 256);
+    mbar_init(acc_empty, 8);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&xf_full[i], 1);
       mbar_init(&xf_free[i], 1);
@@ -677,7 +677,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           // this warpgroup's share of quarter ci is in tensor memory: hand it to the MMA issuer
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&g_full[ci]);
+          __syncwarp();  // every lane's store is fenced before the one arrival of this warp
+          if (lane == 0) mbar_arrive(&g_full[ci]);
           TRACE_EPI(3);
           // ... and the same 32 keys (64 B per row) to the send warps (warps 2-3) through this warp's
           // 2 KB buffer: they read it back transposed and issue the st.async stream, so its
@@ -735,7 +736,8 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
           }
         }
         tc_fence_before();
-        mbar_arrive(acc_empty);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
         ++seg;
         seg_head = false;
       }

@@ -213,3 +213,26 @@ def test_more_pairs_than_the_fused_step_handles_stay_on_the_general_path():
         loss, leaves, s = _step(fn, emb[0], ids[0], 1 / 0.07, pairs, torch.bfloat16)
         _compare(loss, leaves, s, ref.losses[0], ref.grads[0], ref.dscale[0], ref.dscale_gross[0])
     assert fn.steady_steps == 0
+
+
+def test_steady_steps_are_bitwise_reproducible():
+    """The fused step writes every gradient element once (stores, plus scratch tiles summed in a
+    fixed order) and reduces the loss in a fixed order, so repeated steps on the same batch must
+    agree bit for bit.  This doubles as a race detector for the shared-memory hand-offs inside the
+    backward kernel (conversion warps -> send warps -> partner CTA), which compute-sanitizer's
+    racecheck cannot follow because they are ordered by mbarriers."""
+    from mmlearn_b200 import ContrastiveLoss
+
+    n, d = 8192, 512  # 64 x-tiles x 32 key tiles per (pair, side): several tiles per CTA pair
+    emb, ids = synthetic_inputs(n, d)
+    fn = ContrastiveLoss(l2_normalize=True, local_loss=True, gather_with_grad=True)
+    pairs = [("rgb", "text", 1.0)]
+    _step(fn, emb[0], ids[0], 1 / 0.07, pairs, torch.bfloat16)  # general path
+    loss0, leaves0, s0 = _step(fn, emb[0], ids[0], 1 / 0.07, pairs, torch.bfloat16)
+    assert fn.steady_steps == 1
+    for k in range(2, 12):
+        loss, leaves, s = _step(fn, emb[0], ids[0], 1 / 0.07, pairs, torch.bfloat16)
+        assert fn.steady_steps == k
+        assert torch.equal(loss, loss0) and torch.equal(s.grad, s0.grad)
+        for key in leaves:
+            assert torch.equal(leaves[key].grad, leaves0[key].grad), (k, key)
