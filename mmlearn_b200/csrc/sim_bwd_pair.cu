@@ -353,6 +353,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         }
       };
       auto load_dx = [&](int col0, int yt, int kind) {
+#pragma unroll 1
         for (int js = 0; js < BNY / 64; ++js) {
           mbar_wait(&empty[stage], phase ^ 1);
           TRACE(24 + kind * 4 + js, prod_cnt);
@@ -431,6 +432,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
       };
       auto issue_dx_own = [&]() {  // A = own G in tensor memory
         begin_dx();
+#pragma unroll 1
         for (int js = 0; js < BNY / 64; ++js) {
           mbar_wait(&g_full[js], own_cnt & 1);
           tc_fence_after();
@@ -463,6 +465,7 @@ sim_grad_bwd_pair_kernel(const __grid_constant__ TensorMaps maps,
         TRACE(3, peer_cnt);
         fence_proxy_async_smem();  // the partner's stores -> my tensor-core (async proxy) reads
         tc_fence_after();
+#pragma unroll 1
         for (int js = 0; js < BNY / 64; ++js) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
