@@ -99,6 +99,7 @@ struct mmcl_step {
   unsigned long long* d_tickets = nullptr;  // [kFlagChannels] + [1]
   unsigned long long n_push_launches = 0, n_post_launches = 0, n_pack_launches = 0;
   int first_wave = -1;  // modality the pack kernel itself stores into every rank (world > 1)
+  bool fanout_all = false;  // ... or every modality (MMCL_PACK_FANOUT_ALL=1): no pushes in the forward kernel
   unsigned gen = 0, salt = 0;
   unsigned long long seq = 0;  // flag sequence number of the last forward
   // verification
@@ -375,6 +376,10 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
   // others travel under the forward kernel's tensor-core work (its two spare warps per CTA
   // sustain ~270 GB/s, enough to arrive before the phase that needs them).
   s->first_wave = (W > 1 && s->push_order.size() > 1) ? s->push_order[0] : -1;
+  {
+    const char* e = std::getenv("MMCL_PACK_FANOUT_ALL");
+    s->fanout_all = W > 1 && e && std::atoi(e) != 0;
+  }
 
   // ---- backward plan ----
   bwd_begin(&s->bwd, s->d);
@@ -477,8 +482,8 @@ int mmcl_step_create(mmcl_handle* h, const mmcl_step_desc* desc, mmcl_step** out
   }
   // ---- device counters + verification state ----
   DeviceGuard g(h->device);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_tickets), (kFlagChannels + 1) * 8);
-  if (e == cudaSuccess) e = cudaMemset(s->d_tickets, 0, (kFlagChannels + 1) * 8);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_tickets), (kFlagChannels + 2) * 8);
+  if (e == cudaSuccess) e = cudaMemset(s->d_tickets, 0, (kFlagChannels + 2) * 8);
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&s->host), 16);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -604,7 +609,7 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         pm.ids_dst = (W > 1 && s->is_key[m])
                          ? reinterpret_cast<int64_t*>(v.ar + s->ar_ids[m] + size_t(off) * 16)
                          : nullptr;
-        pm.fanout = m == s->first_wave ? 1 : 0;
+        pm.fanout = (m == s->first_wave || s->fanout_all) ? 1 : 0;
         pm.off_rows = s->ar_rows[m] + size_t(off) * d * 2;
         pm.off_inv = s->ar_inv[m] + size_t(off) * 4;
         pm.off_ids = s->ar_ids[m] + size_t(off) * 16;
@@ -619,6 +624,18 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         s->n_pack_launches += 1;
         PL.ticket_target = s->n_pack_launches * (unsigned long long)((b + 7) / 8);
         PL.seq = s->seq;
+        PL.status_chan = -1;
+        if (s->fanout_all) {
+          // a channel every rank's forward kernel waits on (a key modality), released last
+          int ms = s->push_order[0];
+          for (int m : s->push_order)
+            if (s->is_key[m]) ms = m;
+          PL.status_chan = row_chan(ms);
+          PL.status_off = s->ar_status;
+          PL.status_val = status_ok;
+          PL.all_ticket = s->d_tickets + kFlagChannels + 1;
+          PL.all_target = PL.ticket_target * (unsigned long long)s->M;
+        }
       }
       CU(launch_step_pack(PL, st), "mmcl_step_forward (pack)");
     }
@@ -678,7 +695,7 @@ int mmcl_step_forward(mmcl_step* s, int parity, int local_ok, const void* const*
         };
         for (size_t i = 0; i < s->push_order.size(); ++i) {
           const int m = s->push_order[i];
-          if (m == s->first_wave) continue;  // already in every rank's arena (pack kernel)
+          if (m == s->first_wave || s->fanout_all) continue;  // already in every rank's arena (pack kernel)
           const int ch = row_chan(m);
           // a channel shared by several modalities (m >= kMaxRowChannels) is released once, after
           // the last of them

@@ -177,18 +177,34 @@ __global__ void step_pack_kernel(const __grid_constant__ PackLaunch L) {
   }
   if (!md.fanout) return;
   // last block of this modality: release its ready flags on every rank
+  __shared__ int s_last_all;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     const unsigned long long done = atomicAdd(L.tickets + md.chan, 1ull) + 1ull;
     s_last = done == L.ticket_target ? 1 : 0;
-    if (s_last) __threadfence_system();
+    s_last_all = 0;
+    if (L.status_chan >= 0)
+      s_last_all = atomicAdd(L.all_ticket, 1ull) + 1ull == L.all_target ? 1 : 0;
+    if (s_last || s_last_all) __threadfence_system();
   }
   __syncthreads();
-  if (s_last && int(threadIdx.x) < L.world) {
+  if (s_last && md.chan != L.status_chan && int(threadIdx.x) < L.world) {
     __threadfence_system();
     st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[threadIdx.x]) +
                            md.chan * kMaxRanks + L.rank,
+                       L.seq);
+  }
+  if (s_last_all && int(threadIdx.x) < L.world) {
+    // every block of every modality is done: the id comparisons are final
+    unsigned long long sv = L.status_val;
+    for (int p = 0; p < L.P; ++p)
+      if (__ldcg(L.hdr + kHdrBad + p) == (unsigned long long)L.gen) sv &= ~1ull;
+    *reinterpret_cast<unsigned long long*>(L.peers[threadIdx.x] + L.buf_off + L.status_off +
+                                           8ull * L.rank) = sv;
+    __threadfence_system();
+    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(L.peers[threadIdx.x]) +
+                           L.status_chan * kMaxRanks + L.rank,
                        L.seq);
   }
 }

@@ -40,6 +40,13 @@ struct PackLaunch {
   unsigned long long* tickets;        // [kFlagChannels]
   unsigned long long ticket_target;   // pack launches so far x blocks per modality
   unsigned long long seq;
+  // Every modality fanned out by this kernel (no pushes left for the forward kernel): the block
+  // that finishes last OVERALL publishes this rank's status word and only then releases the flags
+  // of `status_chan` (the consumers read the status after they have seen that channel).
+  int status_chan;                    // -1: the forward kernel's push warps publish the status
+  unsigned long long status_off, status_val;
+  unsigned long long* all_ticket;     // counts the blocks of all modalities
+  unsigned long long all_target;
   PackMod mod[kStepMaxMods];
 };
 
