@@ -13,12 +13,16 @@
 // pipe alternates  S(own) | dX(partner's G)  | dX(own G)  with the epilogue of S(own) hidden
 // under dX(partner's G).
 //
-// Per CTA (384 threads, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue of key half 0 (S columns 0-127), warps 8-11 epilogue of key half 1
-// (two warps per SM sub-partition hide the tensor-memory load latency; the ex2 rate of 16/clk/SM
-// is the floor of the epilogue).  Shared memory: 3 stages x 48 KB (X chunk 128x64 + Y box
-// 256x64 for S; 64-key x d/2 boxes for dX), 64 KB staging for the partner's G (K-major,
-// 128-byte swizzle, 4 atoms of 64 keys), column data, barriers.
+// Per CTA (384 threads, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 G send warps
+// (warp 2 also allocates tensor memory), warps 4-7 epilogue of key half 0 (S columns 0-127), warps
+// 8-11 epilogue of key half 1.  The epilogue warps hand every converted 32-key chunk to the send
+// warps through a 2 KB shared-memory buffer per warp (mbarrier hand-shake); the send warps read it
+// back transposed and issue the st.async stream into the partner's staging tile, so the
+// distributed-shared-memory back-pressure (18-20 B/clk, tools/dsmem_rate.cu) never stalls the
+// conversion.  Shared memory: 3 stages x 48 KB (X chunk 128x64 + Y box 256x64 for S; 64-key x d/2
+// boxes for dX), 64 KB staging for the partner's G (K-major, 128-byte swizzle, 4 atoms of 64 keys),
+// 16 KB of hand-off buffers, column data, barriers.  tools/bwd_trace.cu (MMCL_TRACE) stamps the SM
+// clock of every role; DESIGN.md section 4 has the measured phase times.
 // Work: one launch covers a LIST of problems (fused.h, BwdProb: every (pair, side) of the loss).
 // Their (x-tile, d-pass, y-tile) spaces are laid end to end, linearised and cut into equal
 // contiguous ranges, one per CTA pair.  d-passes exist only for d > 512 (each pass covers
